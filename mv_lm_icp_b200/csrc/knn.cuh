@@ -1,0 +1,188 @@
+// knn.cuh -- exact nearest-neighbour correspondence kernel (replaces nanoflann on the hot path).
+//
+// Reference semantics reproduced:
+//   * query transform  g = R_s p + t_s ; q = Rinv_d (g - t_d)   src/internal/frame.cpp:117-118,131,136
+//     in fp64, round-to-nearest after every multiply and add (no FMA contraction), left-fold sums;
+//   * distance         (d0*d0 + d1*d1) + d2*d2 with d = q - p   include/frame.h:70-76, fp64, no FMA;
+//   * result           the dst point minimising that value      nanoflann.hpp:1200-1247 (exact search, eps = 0);
+//     ties (equal fp64 distance) resolve to the LOWEST ORIGINAL INDEX here, whereas nanoflann keeps the first
+//     point its traversal meets (nanoflann.hpp:1210) -- documented deviation, counted by the tests;
+//   * cutoff           sqrt(d2) < (double)thresh                 frame.cpp:142,156.
+//
+// Search structure: implicit binary AABB tree over Morton-sorted leaves (types.cuh).  Pruning is exact:
+// a box's lower bound is evaluated with the SAME rounded operation sequence as the point distance and every
+// operation is monotone, so lb(box) <= d2(point) for every point inside; a subtree is skipped only when
+// lb > best (strict), which also keeps all equal-distance candidates reachable for the tie rule.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include "types.cuh"
+
+namespace mv {
+
+template <bool F32> struct Rec;
+template <> struct Rec<true> {
+  typedef float4 type;
+  static __device__ __forceinline__ void load(const void* base, int64_t i, double& x, double& y, double& z, int& w) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(base) + i);
+    x = (double)r.x; y = (double)r.y; z = (double)r.z; w = __float_as_int(r.w);
+  }
+};
+template <> struct Rec<false> {
+  typedef double4a type;
+  static __device__ __forceinline__ void load(const void* base, int64_t i, double& x, double& y, double& z, int& w) {
+    const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double4a*>(base) + i);
+    const double2 a = __ldg(p), b = __ldg(p + 1);
+    x = a.x; y = a.y; z = b.x; w = (int)__double_as_longlong(b.y);
+  }
+};
+
+__device__ __forceinline__ double d2_rn(double qx, double qy, double qz, double px, double py, double pz) {
+  const double d0 = __dsub_rn(qx, px), d1 = __dsub_rn(qy, py), d2 = __dsub_rn(qz, pz);
+  return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+}
+
+__device__ __forceinline__ double box_lb(const Box* __restrict__ boxes, int node, double qx, double qy, double qz) {
+  const float4* b = reinterpret_cast<const float4*>(boxes + node);
+  const float4 u = __ldg(b), v = __ldg(b + 1);   // u = lo.xyz, hi.x ; v = hi.yz, pad
+  const double dx = fmax(fmax(__dsub_rn((double)u.x, qx), __dsub_rn(qx, (double)u.w)), 0.0);
+  const double dy = fmax(fmax(__dsub_rn((double)u.y, qy), __dsub_rn(qy, (double)v.x)), 0.0);
+  const double dz = fmax(fmax(__dsub_rn((double)u.z, qz), __dsub_rn(qz, (double)v.y)), 0.0);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Exact 1-NN of (qx,qy,qz) in frame fd.  best/bi may carry a seed (a valid candidate and its distance).
+template <bool F32>
+__device__ __forceinline__ void nn_search(const FrameDev& fd, double qx, double qy, double qz, double& best, int& bi) {
+  const int L = fd.n_leaf_pad;
+  int stk_n[20]; double stk_lb[20]; int sp = 0;
+  int node = 1;
+  if (box_lb(fd.boxes, 1, qx, qy, qz) > best) return;
+  while (true) {
+    if (node >= L) {
+      const int64_t b = (int64_t)(node - L) * LEAF;
+      const int cnt = min(LEAF, fd.n - (int)b);
+#pragma unroll 1
+      for (int i = 0; i < cnt; ++i) {
+        double px, py, pz; int pi;
+        Rec<F32>::load(fd.pts_s, b + i, px, py, pz, pi);
+        const double d = d2_rn(qx, qy, qz, px, py, pz);
+        if (d < best || (d == best && pi < bi)) { best = d; bi = pi; }
+      }
+    } else {
+      const int c0 = 2 * node;
+      const double l0 = box_lb(fd.boxes, c0, qx, qy, qz), l1 = box_lb(fd.boxes, c0 + 1, qx, qy, qz);
+      const bool first0 = l0 <= l1;
+      const double ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
+      if (ln <= best) {
+        if (lf <= best) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+        node = first0 ? c0 : c0 + 1;
+        continue;
+      }
+    }
+    // pop
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      if (stk_lb[sp] <= best) { node = stk_n[sp]; found = true; break; }
+    }
+    if (!found) break;
+  }
+}
+
+// One thread per (edge, src point) query; src points are walked in the src frame's Morton order so that the
+// lanes of a warp descend the dst tree together.
+template <bool F32>
+__global__ void __launch_bounds__(KNN_TILE)
+knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
+           const Tile* __restrict__ tiles, int32_t* __restrict__ corr, double* __restrict__ d2out,
+           const int32_t* __restrict__ seed, unsigned long long* __restrict__ edge_count, double thresh) {
+  const Tile t = tiles[blockIdx.x];
+  const EdgeDev e = edges[t.edge];
+  __shared__ EdgeXf sx;
+  __shared__ int s_cnt;
+  {
+    const double* g = reinterpret_cast<const double*>(xfs + t.edge);
+    double* s = reinterpret_cast<double*>(&sx);
+    for (int i = threadIdx.x; i < (int)(sizeof(EdgeXf) / sizeof(double)); i += blockDim.x) s[i] = g[i];
+    if (threadIdx.x == 0) s_cnt = 0;
+  }
+  __syncthreads();
+  const FrameDev fs = frames[e.src];
+  const FrameDev fd = frames[e.dst];
+  const int ks = t.start + threadIdx.x;
+  int inl = 0;
+  if (ks < e.n_src) {
+    double px, py, pz; int orig;
+    Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
+    // g = R_s p + t_s
+    const double gx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[0], px), __dmul_rn(sx.Rs[1], py)), __dmul_rn(sx.Rs[2], pz)), sx.ts[0]);
+    const double gy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[3], px), __dmul_rn(sx.Rs[4], py)), __dmul_rn(sx.Rs[5], pz)), sx.ts[1]);
+    const double gz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[6], px), __dmul_rn(sx.Rs[7], py)), __dmul_rn(sx.Rs[8], pz)), sx.ts[2]);
+    const double ex = __dsub_rn(gx, sx.td[0]), ey = __dsub_rn(gy, sx.td[1]), ez = __dsub_rn(gz, sx.td[2]);
+    const double qx = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[0], ex), __dmul_rn(sx.Rinv[1], ey)), __dmul_rn(sx.Rinv[2], ez));
+    const double qy = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[3], ex), __dmul_rn(sx.Rinv[4], ey)), __dmul_rn(sx.Rinv[5], ez));
+    const double qz = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[6], ex), __dmul_rn(sx.Rinv[7], ey)), __dmul_rn(sx.Rinv[8], ez));
+
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int bi = INT_MAX;
+    if (seed) {   // previous round's match: a valid upper bound, the search stays exact
+      const int s = seed[e.off + orig];
+      const int si = s >= 0 ? s : ~s;
+      if (si >= 0 && si < fd.n) {
+        double sxp, syp, szp; int dummy;
+        Rec<F32>::load(fd.pts_o, si, sxp, syp, szp, dummy);
+        best = d2_rn(qx, qy, qz, sxp, syp, szp); bi = si;
+      }
+    }
+    nn_search<F32>(fd, qx, qy, qz, best, bi);
+    const bool inlier = __dsqrt_rn(best) < thresh;
+    corr[e.off + orig] = inlier ? bi : ~bi;
+    d2out[e.off + orig] = best;
+    inl = inlier ? 1 : 0;
+  }
+  // inlier count of the edge (integer atomics: order-independent)
+  const unsigned m = __ballot_sync(0xffffffffu, inl);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(edge_count + t.edge, (unsigned long long)s_cnt);
+}
+
+template <bool F32>
+__global__ void knn_single_kernel(const FrameDev* __restrict__ frames, int frame, double qx, double qy, double qz,
+                                  long long* out_idx, double* out_d2) {
+  const FrameDev fd = frames[frame];
+  double best = __longlong_as_double(0x7ff0000000000000LL);
+  int bi = INT_MAX;
+  nn_search<F32>(fd, qx, qy, qz, best, bi);
+  *out_idx = bi; *out_d2 = best;
+}
+
+// Per-edge constants from the current poses (poses16: column-major 4x4 per frame), with the reference's
+// arithmetic: general 3x3 inverse by cofactors (frame.cpp:118; Eigen's size-3 inverse).
+__global__ void edge_xf_kernel(const double* __restrict__ poses16, const EdgeDev* __restrict__ edges, int n_edges,
+                               EdgeXf* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const double* Ps = poses16 + 16 * edges[e].src;
+  const double* Pd = poses16 + 16 * edges[e].dst;
+  EdgeXf x;
+  double M[9];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) { x.Rs[3 * i + j] = Ps[4 * j + i]; M[3 * i + j] = Pd[4 * j + i]; }
+    x.ts[i] = Ps[12 + i]; x.td[i] = Pd[12 + i];
+  }
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return __dsub_rn(__dmul_rn(M[3 * i1 + j1], M[3 * i2 + j2]), __dmul_rn(M[3 * i1 + j2], M[3 * i2 + j1]));
+  };
+  const double c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+  const double det = __dadd_rn(__dadd_rn(__dmul_rn(c00, M[0]), __dmul_rn(c10, M[3])), __dmul_rn(c20, M[6]));
+  const double invdet = __ddiv_rn(1.0, det);
+  x.Rinv[0] = __dmul_rn(c00, invdet); x.Rinv[1] = __dmul_rn(c10, invdet); x.Rinv[2] = __dmul_rn(c20, invdet);
+  x.Rinv[3] = __dmul_rn(cof(0, 1), invdet); x.Rinv[4] = __dmul_rn(cof(1, 1), invdet); x.Rinv[5] = __dmul_rn(cof(2, 1), invdet);
+  x.Rinv[6] = __dmul_rn(cof(0, 2), invdet); x.Rinv[7] = __dmul_rn(cof(1, 2), invdet); x.Rinv[8] = __dmul_rn(cof(2, 2), invdet);
+  out[e] = x;
+}
+
+}  // namespace mv

@@ -1,0 +1,161 @@
+// lm_eval.cuh -- residual / Jacobian streaming kernel of the LM step (replaces Ceres' evaluator).
+//
+// Reference semantics: per correspondence (p = src point, q = dst point, n = dst normal)
+//   point-to-point  r = (R_s p + t_s) - (R_k q + t_k)                 include/icp-ceres.h:49-99,143-185,236-275
+//   point-to-plane  r = ((R_s p + t_s) - (R_k q + t_k)) . (R_k n)     include/icp-ceres.h:101-141,187-234,277-316
+//   robust          SoftLOneLoss(a = edge.weight): rho(s) = 2b(sqrt(1+s/b)-1), b = a^2; since rho'' < 0 Ceres'
+//                   corrector scales the block's residuals and Jacobian rows by sqrt(rho')  (icp-ceres.cpp:284,374,449)
+//   cost            1/2 sum rho(|r|^2)   (1/2 sum |r|^2 without loss)
+//
+// Formulation.  Both residuals are invariant under the dst rotation, so they are evaluated in the dst frame:
+// x = T_k^-1 T_s p = R_rel p + t_rel, d = x - q; p2p: r = d, p2plane: r = d . n.  With the canonical body tangent
+// xi = (upsilon, omega) of T_s <- T_s exp(xi):   dr/dxi_s = [m ; p x m],  m = R_rel^T n   (p2plane)
+//                                                 J_s = R_rel [I | -[p]x]               (p2p)
+// and the dst-side Jacobian is J_k = -J_s Ad(T_rel^-1) for every residual, so ONE 6x6 block A = sum w J_s^T J_s,
+// one 6-vector b = sum w J_s^T r and the cost are accumulated per edge (28 doubles); lm_step.cuh expands them to
+// the (s,s),(s,k),(k,k) blocks and maps the canonical tangent to the active parameterisation (tangent_map()).
+// Bytes per correspondence: idx 4 + src 16 + dst 16 (+ normal 16) = 36 / 52 B in the fp32-storage mode.
+#pragma once
+#include <cuda_runtime.h>
+#include "knn.cuh"
+#include "se3_math.cuh"
+#include "types.cuh"
+
+namespace mv {
+
+enum { COST_P2P = 0, COST_P2PLANE = 1, COST_MIXED = 2 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// partial[tile][NBLK]: A upper triangle row-major (21), b (6), cost (1)
+template <bool F32, int COST>
+__global__ void __launch_bounds__(EVAL_THREADS)
+lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
+               int tile_len, const int32_t* __restrict__ corr, const Rt* __restrict__ frame_Rt,
+               const float* __restrict__ weight, int robust, double* __restrict__ partial) {
+  const Tile t = tiles[blockIdx.x];
+  const EdgeDev e = edges[t.edge];
+  __shared__ double sRel[12];
+  __shared__ double sred[EVAL_THREADS / 32][NBLK];
+  if (threadIdx.x == 0) {
+    const Rt a = frame_Rt[e.src], k = frame_Rt[e.dst];
+    double R[9]; matTmul(k.R, a.R, R);
+    const double dt[3] = {a.t[0] - k.t[0], a.t[1] - k.t[1], a.t[2] - k.t[2]};
+    double tr[3]; matTvec(k.R, dt, tr);
+    for (int i = 0; i < 9; ++i) sRel[i] = R[i];
+    sRel[9] = tr[0]; sRel[10] = tr[1]; sRel[11] = tr[2];
+  }
+  __syncthreads();
+  double R[9], tr[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = sRel[i];
+  tr[0] = sRel[9]; tr[1] = sRel[10]; tr[2] = sRel[11];
+  const double a_w = (double)weight[t.edge];
+  const double bb = a_w * a_w, cc = 1.0 / bb;
+
+  const FrameDev fs = frames[e.src];
+  const FrameDev fd = frames[e.dst];
+  double A[21], g[6], cost = 0.0;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) A[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) g[i] = 0.0;
+  double sw = 0.0, swp[3] = {0, 0, 0}, swpp[6] = {0, 0, 0, 0, 0, 0};   // p2p structure: sum w, sum w p, sum w p p^T
+
+  const int end = min(t.start + tile_len, e.n_src);
+  for (int k = t.start + threadIdx.x; k < end; k += EVAL_THREADS) {
+    const int c = __ldg(corr + e.off + k);
+    if (c < 0) continue;
+    double px, py, pz, qx, qy, qz; int dummy;
+    Rec<F32>::load(fs.pts_o, k, px, py, pz, dummy);
+    Rec<F32>::load(fd.pts_o, c, qx, qy, qz, dummy);
+    const double x0 = R[0] * px + R[1] * py + R[2] * pz + tr[0];
+    const double x1 = R[3] * px + R[4] * py + R[5] * pz + tr[1];
+    const double x2 = R[6] * px + R[7] * py + R[8] * pz + tr[2];
+    const double d0 = x0 - qx, d1 = x1 - qy, d2 = x2 - qz;
+    if (COST == COST_P2PLANE || COST == COST_MIXED) {
+      double nx, ny, nz;
+      Rec<F32>::load(fd.nor_o, c, nx, ny, nz, dummy);
+      const double r = d0 * nx + d1 * ny + d2 * nz;
+      const double s = r * r;
+      double w = 1.0;
+      if (robust) { const double tt = sqrt(1.0 + s * cc); w = 1.0 / tt; cost += bb * (tt - 1.0); }
+      else cost += 0.5 * s;
+      double a[6];
+      a[0] = R[0] * nx + R[3] * ny + R[6] * nz;   // m = R_rel^T n
+      a[1] = R[1] * nx + R[4] * ny + R[7] * nz;
+      a[2] = R[2] * nx + R[5] * ny + R[8] * nz;
+      a[3] = py * a[2] - pz * a[1];               // p x m
+      a[4] = pz * a[0] - px * a[2];
+      a[5] = px * a[1] - py * a[0];
+      const double wr = w * r;
+      int idx = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double wa = w * a[i];
+        g[i] += wr * a[i];
+#pragma unroll
+        for (int j = i; j < 6; ++j) A[idx++] += wa * a[j];
+      }
+    }
+    if (COST == COST_P2P || COST == COST_MIXED) {
+      const double s = d0 * d0 + d1 * d1 + d2 * d2;
+      double w = 1.0;
+      if (robust) { const double tt = sqrt(1.0 + s * cc); w = 1.0 / tt; cost += bb * (tt - 1.0); }
+      else cost += 0.5 * s;
+      const double u0 = R[0] * d0 + R[3] * d1 + R[6] * d2;   // u = R_rel^T d
+      const double u1 = R[1] * d0 + R[4] * d1 + R[7] * d2;
+      const double u2 = R[2] * d0 + R[5] * d1 + R[8] * d2;
+      g[0] += w * u0; g[1] += w * u1; g[2] += w * u2;
+      g[3] += w * (py * u2 - pz * u1); g[4] += w * (pz * u0 - px * u2); g[5] += w * (px * u1 - py * u0);
+      sw += w;
+      const double wx = w * px, wy = w * py, wz = w * pz;
+      swp[0] += wx; swp[1] += wy; swp[2] += wz;
+      swpp[0] += wx * px; swpp[1] += wx * py; swpp[2] += wx * pz; swpp[3] += wy * py; swpp[4] += wy * pz; swpp[5] += wz * pz;
+    }
+  }
+  if (COST == COST_P2P || COST == COST_MIXED) {
+    // sum w J^T J with J = R_rel [I | -[p]x]:  [[w I, -w[p]x], [w[p]x, w(|p|^2 I - p p^T)]]
+    // U(i,j): index of (i,j), i <= j, in the row-major upper triangle
+    auto U = [](int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); };
+    A[U(0, 0)] += sw; A[U(1, 1)] += sw; A[U(2, 2)] += sw;
+    A[U(0, 4)] += swp[2];  A[U(0, 5)] += -swp[1];
+    A[U(1, 3)] += -swp[2]; A[U(1, 5)] += swp[0];
+    A[U(2, 3)] += swp[1];  A[U(2, 4)] += -swp[0];
+    const double trp = swpp[0] + swpp[3] + swpp[5];
+    A[U(3, 3)] += trp - swpp[0]; A[U(3, 4)] += -swpp[1]; A[U(3, 5)] += -swpp[2];
+    A[U(4, 4)] += trp - swpp[3]; A[U(4, 5)] += -swpp[4];
+    A[U(5, 5)] += trp - swpp[5];
+  }
+
+  // block reduction: warp shuffles, then one value per warp through shared memory, fixed order
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) { const double v = warp_sum(A[i]); if (lane == 0) sred[wid][i] = v; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { const double v = warp_sum(g[i]); if (lane == 0) sred[wid][21 + i] = v; }
+  { const double v = warp_sum(cost); if (lane == 0) sred[wid][27] = v; }
+  __syncthreads();
+  if (threadIdx.x < NBLK) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < EVAL_THREADS / 32; ++w) v += sred[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * NBLK + threadIdx.x] = v;
+  }
+}
+
+// blocks[e][NBLK] = sum of the edge's tile partials in tile order (deterministic); zero for edges not owned.
+__global__ void lm_reduce_kernel(const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
+                                 double* __restrict__ blocks) {
+  const int e = blockIdx.x, j = threadIdx.x;
+  if (j >= NBLK) return;
+  double v = 0.0;
+  for (int t = edge_tile_begin[e]; t < edge_tile_begin[e + 1]; ++t) v += partial[(size_t)t * NBLK + j];
+  blocks[(size_t)e * NBLK + j] = v;
+}
+
+}  // namespace mv

@@ -1,0 +1,361 @@
+// lm_step.cuh -- the Levenberg-Marquardt trust-region state machine, one CTA, entirely on the device.
+//
+// Replaces ceres::Solve(getOptionsMedium(), ...) (src/internal/icp-ceres.cpp:66-95): LEVENBERG_MARQUARDT trust
+// region, normal equations + Cholesky (SPARSE_NORMAL_CHOLESKY in the reference; dense here, <= 6(M-1) unknowns),
+// Jacobi scaling, Ceres' step acceptance / radius update / termination tests (Ceres 1.13
+// semantics [ext-knowledge], the same contract the CPU oracle restates).
+//
+// One invocation consumes the per-edge blocks evaluated at the point the previous invocation proposed
+// (residuals AND Jacobian blocks are evaluated together, so an accepted candidate needs no second pass over the
+// correspondences), decides accept / reject / terminate, then solves for and writes the next candidate.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/mvicp.h"
+#include "se3_math.cuh"
+#include "types.cuh"
+
+namespace mv {
+
+constexpr int STEP_THREADS = 512;
+
+struct LmState {
+  mvicp_lm_options opt;
+  int32_t param, cost_kind, robust, M, E, F, n, G;
+  int32_t phase, done, termination, iteration, n_success, n_invalid, n_evals, n_solves, reuse_diagonal, nonrigid;
+  double radius, decrease_factor, x_cost, cand_cost, x_norm, initial_cost, model_cost_change, step_norm, gmax;
+};
+
+struct LmWork {
+  LmState* S;
+  const EdgeDev* edges;
+  const double* blocks;      // [E][NBLK] at the evaluation point (summed over ranks)
+  double* x;                 // [M][7] accepted point (all frames)
+  double* cand;              // [M][7] evaluation point / next candidate
+  Rt* Rt_eval;               // [M]
+  double* K_eval;            // [M][36]
+  const int32_t* col;        // [M] first local column or -1
+  // block-sparse gather lists (host-built, deterministic order)
+  const int32_t* hb_ptr; const int32_t* hb_row; const int32_t* hb_col; const int32_t* hc_edge; const int32_t* hc_sub; int32_t n_hblocks;
+  const int32_t* gb_ptr; const int32_t* gc_edge; const int32_t* gc_side;   // per frame
+  double *H, *g, *Hc, *gc, *scale, *diag, *Lg, *rhs, *step, *Bs, *ABs, *Hp, *gp;
+  double* poses16;
+  int32_t l_in_smem;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < STEP_THREADS / 32; ++w) s += red[w]; red[32] = s; }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < STEP_THREADS / 32; ++w) s = fmax(s, red[w]); red[32] = s; }
+  __syncthreads();
+  return red[32];
+}
+
+// Per-frame set-up before the first evaluation: poses -> parameters, functor rotation, tangent map.
+__global__ void lm_init_kernel(LmWork w) {
+  LmState* S = w.S;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= S->M) return;
+  double x[7] = {0, 0, 0, 0, 0, 0, 0};
+  param_of_pose(S->param, w.poses16 + 16 * f, x);
+  if (S->param != PARAM_AA) {
+    const double n2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+    if (!(fabs(n2 - 1.0) <= 1e-9)) atomicExch(&S->nonrigid, 1);
+  }
+  Rt a; Rt_of_param(S->param, x, &a);
+  double K[36]; tangent_map(S->param, x, &a, K);
+  for (int i = 0; i < 7; ++i) { w.x[7 * f + i] = x[i]; w.cand[7 * f + i] = x[i]; }
+  w.Rt_eval[f] = a;
+  for (int i = 0; i < 36; ++i) w.K_eval[36 * f + i] = K[i];
+}
+
+// ---- dense Cholesky solve on L (n x n row-major, lower part used), rhs overwritten by the solution ----------
+__device__ bool chol_solve(double* L, double* y, int n) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  for (int j = 0; j < n; ++j) {
+    __syncthreads();
+    const double d = L[(size_t)j * n + j];
+    if (!(d > 0.0) || !isfinite(d)) return false;     // uniform: every thread reads the same value
+    const double sd = sqrt(d);
+    __syncthreads();
+    for (int i = j + tid; i < n; i += T) L[(size_t)i * n + j] = (i == j) ? sd : L[(size_t)i * n + j] / sd;
+    __syncthreads();
+    const int m = n - 1 - j;
+    for (int idx = tid; idx < m * m; idx += T) {
+      const int r = idx / m, c = idx - r * m;
+      if (c <= r) L[(size_t)(j + 1 + r) * n + j + 1 + c] -= L[(size_t)(j + 1 + r) * n + j] * L[(size_t)(j + 1 + c) * n + j];
+    }
+  }
+  for (int j = 0; j < n; ++j) {          // L z = y
+    __syncthreads();
+    const double yj = y[j] / L[(size_t)j * n + j];
+    __syncthreads();
+    if (tid == 0) y[j] = yj;
+    for (int i = j + 1 + tid; i < n; i += T) y[i] -= L[(size_t)i * n + j] * yj;
+  }
+  for (int j = n - 1; j >= 0; --j) {     // L^T x = z
+    __syncthreads();
+    const double yj = y[j] / L[(size_t)j * n + j];
+    __syncthreads();
+    if (tid == 0) y[j] = yj;
+    for (int i = tid; i < j; i += T) y[i] -= L[(size_t)j * n + i] * yj;
+  }
+  __syncthreads();
+  return true;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
+  extern __shared__ double smem[];
+  __shared__ double red[40];
+  __shared__ int s_flag;
+  LmState* S = w.S;
+  if (S->done) return;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = S->n, M = S->M, E = S->E, param = S->param;
+  double* L = w.l_in_smem ? smem : w.Lg;
+
+  // ================= 1. assemble Hc, gc, cost at the evaluation point ===============================
+  // B_e = [K_s | -Q_e K_k] (6x12), Q_e = Ad(T_rel^-1) = [[R^T, -R^T [t]x], [0, R^T]]
+  for (int e = tid; e < E; e += T) {
+    const Rt a = w.Rt_eval[w.edges[e].src], k = w.Rt_eval[w.edges[e].dst];
+    double R[9]; matTmul(k.R, a.R, R);
+    const double dt[3] = {a.t[0] - k.t[0], a.t[1] - k.t[1], a.t[2] - k.t[2]};
+    double t[3]; matTvec(k.R, dt, t);
+    const double tx[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+    double Rt_[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt_[3 * i + j] = R[3 * j + i];
+    double RtTx[9]; matmul(Rt_, tx, RtTx);
+    double Q[36];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        Q[6 * i + j] = Rt_[3 * i + j]; Q[6 * i + 3 + j] = -RtTx[3 * i + j];
+        Q[6 * (3 + i) + j] = 0.0;      Q[6 * (3 + i) + 3 + j] = Rt_[3 * i + j];
+      }
+    const double* Ks = w.K_eval + 36 * w.edges[e].src;
+    const double* Kk = w.K_eval + 36 * w.edges[e].dst;
+    double* B = w.Bs + 72 * e;
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        B[12 * i + j] = Ks[6 * i + j];
+        double s = 0; for (int m = 0; m < 6; ++m) s += Q[6 * i + m] * Kk[6 * m + j];
+        B[12 * i + 6 + j] = -s;
+      }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < E * 72; idx += T) {      // AB = A B
+    const int e = idx / 72, r = idx - 72 * e, i = r / 12, j = r - 12 * i;
+    const double* blk = w.blocks + (size_t)NBLK * e;
+    const double* B = w.Bs + 72 * e;
+    double s = 0;
+    for (int m = 0; m < 6; ++m) {
+      const int a = min(i, m), b = max(i, m);
+      s += blk[a * 6 - (a * (a - 1)) / 2 + (b - a)] * B[12 * m + j];
+    }
+    w.ABs[idx] = s;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < E * 156; idx += T) {     // Hp = B^T A B (144), gp = B^T b (12)
+    const int e = idx / 156, r = idx - 156 * e;
+    const double* B = w.Bs + 72 * e;
+    if (r < 144) {
+      const int a = r / 12, b = r - 12 * a;
+      const double* AB = w.ABs + 72 * e;
+      double s = 0; for (int i = 0; i < 6; ++i) s += B[12 * i + a] * AB[12 * i + b];
+      w.Hp[144 * e + r] = s;
+    } else {
+      const int a = r - 144;
+      const double* bv = w.blocks + (size_t)NBLK * e + 21;
+      double s = 0; for (int i = 0; i < 6; ++i) s += B[12 * i + a] * bv[i];
+      w.gp[12 * e + a] = s;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += T) w.Hc[idx] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < w.n_hblocks * 36; idx += T) {   // gather into the dense matrix, fixed order
+    const int b = idx / 36, r = idx - 36 * b, i = r / 6, j = r - 6 * i;
+    double s = 0;
+    for (int c = w.hb_ptr[b]; c < w.hb_ptr[b + 1]; ++c) {
+      const int e = w.hc_edge[c], sub = w.hc_sub[c];   // sub: 0 ss, 1 sk, 2 ks, 3 kk
+      s += w.Hp[144 * e + (6 * (sub >> 1) + i) * 12 + 6 * (sub & 1) + j];
+    }
+    w.Hc[(size_t)(w.hb_row[b] + i) * n + w.hb_col[b] + j] = s;
+  }
+  for (int idx = tid; idx < M * 6; idx += T) {
+    const int f = idx / 6, i = idx - 6 * f;
+    if (w.col[f] < 0) continue;
+    double s = 0;
+    for (int c = w.gb_ptr[f]; c < w.gb_ptr[f + 1]; ++c) s += w.gp[12 * w.gc_edge[c] + 6 * w.gc_side[c] + i];
+    w.gc[w.col[f] + i] = s;
+  }
+  __syncthreads();
+  double eval_cost = 0.0;
+  if (tid == 0) { for (int e = 0; e < E; ++e) eval_cost += w.blocks[(size_t)NBLK * e + 27]; red[33] = eval_cost; }
+  __syncthreads();
+  eval_cost = red[33];
+
+  // ================= 2. accept / reject / terminate =================================================
+  bool take = false;    // the evaluation point becomes the accepted point
+  if (tid == 0) {
+    s_flag = 0;
+    S->n_evals += 1;
+    if (!isfinite(eval_cost)) {
+      if (S->phase == 0) { S->done = 1; S->termination = MVICP_TERM_EVAL_FAILURE; }
+      else {   // non-finite candidate cost: Ceres treats the step as invalid
+        S->n_invalid += 1;
+        if (S->n_invalid >= S->opt.max_num_consecutive_invalid_steps) { S->done = 1; S->termination = MVICP_TERM_INVALID_STEPS; }
+        S->radius = S->radius / S->decrease_factor; S->decrease_factor *= 2.0; S->reuse_diagonal = 1;
+      }
+    } else if (S->phase == 0) {
+      S->x_cost = eval_cost; S->initial_cost = eval_cost; s_flag = 1;
+    } else {
+      S->cand_cost = eval_cost;
+      if (S->step_norm <= S->opt.parameter_tolerance * (S->x_norm + S->opt.parameter_tolerance)) {
+        S->done = 1; S->termination = MVICP_TERM_PARAMETER_TOLERANCE;
+      } else if (fabs(S->x_cost - eval_cost) <= S->opt.function_tolerance * S->x_cost) {
+        S->done = 1; S->termination = MVICP_TERM_FUNCTION_TOLERANCE;
+      } else {
+        const double rho = (S->x_cost - eval_cost) / S->model_cost_change;
+        if (rho > S->opt.min_relative_decrease) {
+          s_flag = 1; S->n_success += 1; S->x_cost = eval_cost;
+          const double q = 2.0 * rho - 1.0;
+          S->radius = fmin(S->opt.max_trust_region_radius, S->radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
+          S->decrease_factor = 2.0; S->reuse_diagonal = 0;
+        } else {
+          S->radius = S->radius / S->decrease_factor; S->decrease_factor *= 2.0; S->reuse_diagonal = 1;
+          if (S->radius < S->opt.min_trust_region_radius) { S->done = 1; S->termination = MVICP_TERM_MIN_RADIUS; }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  take = s_flag != 0;
+  if (take) {
+    for (int idx = tid; idx < n * n; idx += T) w.H[idx] = w.Hc[idx];
+    for (int idx = tid; idx < n; idx += T) w.g[idx] = w.gc[idx];
+    for (int idx = tid; idx < M * 7; idx += T) w.x[idx] = w.cand[idx];
+    __syncthreads();
+    if (S->phase == 0)
+      for (int j = tid; j < n; j += T) w.scale[j] = S->opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(w.H[(size_t)j * n + j])) : 1.0;
+    // x_norm over the free blocks, and the gradient test |x - Plus(x, -g)|_inf
+    double xs = 0.0, gm = 0.0;
+    for (int f = tid; f < M; f += T) {
+      if (w.col[f] < 0) continue;
+      const int G = S->G;
+      double xf[7], ng[6], xp[7];
+      for (int i = 0; i < G; ++i) { xf[i] = w.x[7 * f + i]; xs += xf[i] * xf[i]; }
+      for (int i = 0; i < 6; ++i) ng[i] = -w.g[w.col[f] + i];
+      param_plus(param, xf, ng, xp);
+      for (int i = 0; i < G; ++i) gm = fmax(gm, fabs(xf[i] - xp[i]));
+    }
+    xs = block_sum(xs, red);
+    gm = block_max(gm, red);
+    if (tid == 0) {
+      S->x_norm = sqrt(xs); S->gmax = gm;
+      if (gm <= S->opt.gradient_tolerance) { S->done = 1; S->termination = MVICP_TERM_GRADIENT_TOLERANCE; }
+      if (S->phase == 0) { S->phase = 1; S->iteration = 0; S->reuse_diagonal = 0; }
+    }
+    __syncthreads();
+  }
+
+  // ================= 3. next trust-region step ======================================================
+  while (!S->done) {
+    __syncthreads();
+    if (S->iteration >= S->opt.max_num_iterations) {
+      __syncthreads();
+      if (tid == 0) { S->done = 1; S->termination = MVICP_TERM_MAX_ITERATIONS; }
+      __syncthreads();
+      break;
+    }
+    const int reuse = S->reuse_diagonal;
+    const double radius = S->radius;
+    __syncthreads();
+    if (!reuse)
+      for (int j = tid; j < n; j += T) {
+        const double d = w.scale[j] * w.scale[j] * w.H[(size_t)j * n + j];
+        w.diag[j] = fmin(fmax(d, S->opt.min_lm_diagonal), S->opt.max_lm_diagonal);
+      }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += T) {
+      const int i = idx / n, j = idx - i * n;
+      double v = w.scale[i] * w.H[idx] * w.scale[j];
+      if (i == j) { const double ld = sqrt(w.diag[i] / radius); v += ld * ld; }
+      L[idx] = v;
+    }
+    for (int j = tid; j < n; j += T) w.rhs[j] = w.scale[j] * w.g[j];
+    __syncthreads();
+    bool ok = chol_solve(L, w.rhs, n);
+    double bad = 0.0;
+    if (ok) for (int j = tid; j < n; j += T) if (!isfinite(w.rhs[j])) bad = 1.0;
+    bad = block_sum(bad, red);
+    ok = ok && (bad == 0.0);
+    double mcc = 0.0;
+    if (ok) {
+      for (int j = tid; j < n; j += T) w.step[j] = -w.rhs[j];
+      __syncthreads();
+      double acc = 0.0;   // -(s.g~) - 1/2 s^T H~ s
+      for (int i = tid; i < n; i += T) {
+        double row = 0.0;
+        for (int j = 0; j < n; ++j) row += w.H[(size_t)i * n + j] * w.scale[j] * w.step[j];
+        acc += -w.step[i] * w.scale[i] * w.g[i] - 0.5 * w.step[i] * w.scale[i] * row;
+      }
+      mcc = block_sum(acc, red);
+    }
+    const bool valid = ok && (mcc > 0.0);
+    __syncthreads();
+    if (tid == 0) {
+      S->iteration += 1; S->n_solves += 1; S->reuse_diagonal = 1; S->model_cost_change = mcc;
+      if (!valid) {
+        S->n_invalid += 1;
+        if (S->n_invalid >= S->opt.max_num_consecutive_invalid_steps) { S->done = 1; S->termination = MVICP_TERM_INVALID_STEPS; }
+        S->radius = S->radius / S->decrease_factor; S->decrease_factor *= 2.0;
+      } else S->n_invalid = 0;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    // candidate = Plus(x, step * scale) per free frame; step norm in the ambient space
+    double sn = 0.0;
+    for (int f = tid; f < M; f += T) {
+      const int G = S->G;
+      double xf[7], d[6], xp[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int i = 0; i < 7; ++i) xf[i] = w.x[7 * f + i];
+      if (w.col[f] >= 0) {
+        for (int i = 0; i < 6; ++i) d[i] = w.step[w.col[f] + i] * w.scale[w.col[f] + i];
+        param_plus(param, xf, d, xp);
+        for (int i = 0; i < G; ++i) sn += (xf[i] - xp[i]) * (xf[i] - xp[i]);
+      } else for (int i = 0; i < 7; ++i) xp[i] = xf[i];
+      for (int i = 0; i < 7; ++i) w.cand[7 * f + i] = xp[i];
+      Rt a; Rt_of_param(param, xp, &a);
+      w.Rt_eval[f] = a;
+      double K[36]; tangent_map(param, xp, &a, K);
+      for (int i = 0; i < 36; ++i) w.K_eval[36 * f + i] = K[i];
+    }
+    sn = block_sum(sn, red);
+    if (tid == 0) S->step_norm = sqrt(sn);
+    __syncthreads();
+    break;
+  }
+  __syncthreads();
+  // ================= 4. on termination: write every frame's pose back (icp-ceres.cpp:318-322,392-394,472-474)
+  if (S->done) {
+    for (int f = tid; f < M; f += T) {
+      double xf[7]; for (int i = 0; i < 7; ++i) xf[i] = w.x[7 * f + i];
+      pose_of_param(param, xf, w.poses16 + 16 * f);
+    }
+  }
+}
+
+}  // namespace mv

@@ -1,0 +1,755 @@
+// mvicp.cu -- context, host orchestration and the C ABI of libmvicp.so (include/mvicp.h).
+//
+// Host side stays thin C++: it owns device buffers, builds the per-frame search structure once, enqueues the
+// kernels of knn.cuh / select.cuh / lm_eval.cuh / lm_step.cuh on one stream, and (multi-GPU) calls NCCL between
+// them.  No CPU fallback exists: every compute entry point fails with MVICP_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mvicp.h"
+#include "knn.cuh"
+#include "lm_eval.cuh"
+#include "lm_step.cuh"
+#include "se3_math.cuh"
+#include "select.cuh"
+#include "types.cuh"
+
+using namespace mv;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) return fail(MVICP_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define NC(call)                                                                                              \
+  do {                                                                                                        \
+    ncclResult_t r_ = (call);                                                                                 \
+    if (r_ != ncclSuccess) return fail(MVICP_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+  } while (0)
+#define RET(call) do { int r__ = (call); if (r__ != MVICP_OK) return r__; } while (0)
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return MVICP_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    CU(cudaMalloc(&p, bytes ? bytes : 16));
+    cap = bytes ? bytes : 16;
+    return MVICP_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct mvicp_ctx {
+  int device = 0, flags = 0;
+  cudaStream_t stream = nullptr; bool own_stream = false;
+  int rank = 0, world = 1; ncclComm_t comm = nullptr;
+  // frames
+  int M = 0; bool f32 = true; bool have_normals = true;
+  std::vector<int64_t> n_pts;
+  std::vector<FrameDev> h_frames;
+  std::vector<void*> frame_allocs;
+  DevBuf d_frames, d_poses;
+  std::vector<uint8_t> fixed;
+  std::vector<double> h_poses;   // mirror of the last set/get (pose graph construction is host side)
+  // graph
+  int E = 0;
+  std::vector<EdgeDev> h_edges;
+  DevBuf d_edges, d_xf, d_corr, d_d2, d_count, d_sel, d_hist, d_weight, d_median;
+  DevBuf d_knn_tiles, d_eval_tiles, d_edge_tile_begin, d_partial, d_blocks;
+  int n_knn_tiles = 0, n_eval_tiles = 0, eval_tile_len = EVAL_TILE;
+  int64_t total_slots = 0;
+  bool have_corr = false;      // corr[] holds a previous round (usable as seeds)
+  std::vector<float> h_weight; std::vector<unsigned long long> h_count;
+  // LM
+  DevBuf d_state, d_x, d_cand, d_Rt, d_K, d_col, d_H, d_g, d_Hc, d_gc, d_scale, d_diag, d_L, d_rhs, d_step,
+      d_Bs, d_ABs, d_Hp, d_gp, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather;
+  int n_free = 0, n_hblocks = 0;
+  std::vector<int32_t> h_col;
+  int32_t* h_done = nullptr;   // pinned
+  // stats
+  mvicp_stats stats{};
+  cudaEvent_t ev[8]{};
+  bool ev_knn = false, ev_lm = false;
+  float lm_eval_acc = 0.f;
+};
+
+static inline int owner_of(const mvicp_ctx* c, int frame) { return (int)(((int64_t)frame * c->world) / std::max(1, c->M)); }
+
+// =================================================================================================
+// one-time per-frame search structure (replaces the lazily built nanoflann index, frame.cpp:188-193)
+// =================================================================================================
+static inline uint64_t spread21(uint64_t v) {   // 21 bits -> every third bit
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+static inline float f_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
+static inline float f_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
+
+struct HostFrameBuild {
+  std::vector<int32_t> order;      // Morton order -> original index
+  std::vector<Box> boxes;
+  int n_leaf_pad = 1;
+};
+
+static void build_frame(const double* pts, int64_t n, HostFrameBuild& out) {
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], pts[3 * i + a]); hi[a] = std::max(hi[a], pts[3 * i + a]); }
+  double ext = 0; for (int a = 0; a < 3; ++a) ext = std::max(ext, hi[a] - lo[a]);
+  const double sc = ext > 0 ? 2097151.0 / ext : 0.0;
+  std::vector<std::pair<uint64_t, int32_t>> keyed(n);
+  for (int64_t i = 0; i < n; ++i) {
+    uint64_t c[3];
+    for (int a = 0; a < 3; ++a) {
+      double v = (pts[3 * i + a] - lo[a]) * sc;
+      c[a] = (uint64_t)std::min(2097151.0, std::max(0.0, v));
+    }
+    keyed[i] = {spread21(c[0]) | spread21(c[1]) << 1 | spread21(c[2]) << 2, (int32_t)i};
+  }
+  std::sort(keyed.begin(), keyed.end());
+  out.order.resize(n);
+  for (int64_t i = 0; i < n; ++i) out.order[i] = keyed[i].second;
+  const int64_t n_leaf = std::max<int64_t>(1, (n + LEAF - 1) / LEAF);
+  int L = 1; while (L < n_leaf) L <<= 1;
+  out.n_leaf_pad = L;
+  out.boxes.assign((size_t)2 * L, Box{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}, {0, 0}});
+  for (int64_t l = 0; l < n_leaf; ++l) {
+    Box& b = out.boxes[L + l];
+    for (int64_t i = l * LEAF; i < std::min<int64_t>(n, (l + 1) * LEAF); ++i)
+      for (int a = 0; a < 3; ++a) {
+        const double v = pts[3 * (int64_t)out.order[i] + a];
+        b.lo[a] = std::min(b.lo[a], f_down(v)); b.hi[a] = std::max(b.hi[a], f_up(v));
+      }
+  }
+  for (int i = L - 1; i >= 1; --i)
+    for (int a = 0; a < 3; ++a) {
+      out.boxes[i].lo[a] = std::min(out.boxes[2 * i].lo[a], out.boxes[2 * i + 1].lo[a]);
+      out.boxes[i].hi[a] = std::max(out.boxes[2 * i].hi[a], out.boxes[2 * i + 1].hi[a]);
+    }
+}
+
+static bool all_fp32(const double* v, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) if ((double)(float)v[i] != v[i]) return false;
+  return true;
+}
+
+static void pack_records(bool f32, const double* xyz, const int32_t* order, const int32_t* wfield, int64_t n, void* out) {
+  // record i <- point order[i] (or i when order == null); .w <- wfield[i] bits (or 0)
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t j = order ? order[i] : i;
+    const int32_t w = wfield ? wfield[i] : 0;
+    if (f32) {
+      float4 r; r.x = (float)xyz[3 * j]; r.y = (float)xyz[3 * j + 1]; r.z = (float)xyz[3 * j + 2];
+      std::memcpy(&r.w, &w, 4);
+      reinterpret_cast<float4*>(out)[i] = r;
+    } else {
+      double4a r; r.x = xyz[3 * j]; r.y = xyz[3 * j + 1]; r.z = xyz[3 * j + 2];
+      const long long wl = w; std::memcpy(&r.w, &wl, 8);
+      reinterpret_cast<double4a*>(out)[i] = r;
+    }
+  }
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int mvicp_abi_version(void) { return 1; }
+const char* mvicp_last_error(void) { return g_err.c_str(); }
+
+void mvicp_default_lm_options(mvicp_lm_options* o) {
+  o->max_num_iterations = 50; o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1; o->reserved = 0;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+}
+
+int mvicp_create(const mvicp_config* cfg, mvicp_ctx** out) {
+  if (!out) return fail(MVICP_ERR_INVALID, "mvicp_create: out is null");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(MVICP_ERR_CUDA, "mvicp_create: no CUDA device (%s); this engine has no CPU path", cudaGetErrorString(e));
+  mvicp_ctx* c = new mvicp_ctx();
+  c->device = cfg ? cfg->device : 0;
+  c->flags = cfg ? cfg->flags : 0;
+  if (c->device < 0 || c->device >= ndev) { const int d = c->device; delete c; return fail(MVICP_ERR_INVALID, "device %d out of range", d); }
+  CU(cudaSetDevice(c->device));
+  if (cfg && cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+  else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+  CU(cudaMallocHost((void**)&c->h_done, 64));
+  *out = c;
+  return MVICP_OK;
+}
+
+void mvicp_destroy(mvicp_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm) ncclCommDestroy(c->comm);
+  for (void* p : c->frame_allocs) cudaFree(p);
+  DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
+                    &c->d_weight, &c->d_median, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
+                    &c->d_blocks, &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
+                    &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_Bs, &c->d_ABs, &c->d_Hp, &c->d_gp,
+                    &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
+                    &c->d_gc_side, &c->d_posegather};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->h_done) cudaFreeHost(c->h_done);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const double* const* nor, const int64_t* n_pts) {
+  if (!c || M <= 0 || !pts || !n_pts) return fail(MVICP_ERR_INVALID, "mvicp_set_frames: bad arguments");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  for (void* p : c->frame_allocs) cudaFree(p);
+  c->frame_allocs.clear();
+  c->M = M; c->n_pts.assign(n_pts, n_pts + M);
+  c->have_normals = true;
+  bool f32 = true;
+  for (int f = 0; f < M; ++f) {
+    if (n_pts[f] <= 0) return fail(MVICP_ERR_EMPTY, "frame %d has no points (nanoflann would throw, nanoflann.hpp:904)", f);
+    if (n_pts[f] > (int64_t)INT32_MAX / 2) return fail(MVICP_ERR_INVALID, "frame %d too large", f);
+    if (!pts[f]) return fail(MVICP_ERR_INVALID, "frame %d: null points", f);
+    if (!nor || !nor[f]) c->have_normals = false;
+    f32 = f32 && all_fp32(pts[f], 3 * n_pts[f]) && (!nor || !nor[f] || all_fp32(nor[f], 3 * n_pts[f]));
+  }
+  c->f32 = f32;
+  const size_t rec = f32 ? sizeof(float4) : sizeof(double4a);
+  std::vector<HostFrameBuild> builds(M);
+  {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    std::vector<std::thread> pool;
+    std::atomic<int> next{0};
+    for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)M); ++t)
+      pool.emplace_back([&]() { for (int f; (f = next.fetch_add(1)) < M;) build_frame(pts[f], n_pts[f], builds[f]); });
+    for (auto& th : pool) th.join();
+  }
+  c->h_frames.assign(M, FrameDev{});
+  std::vector<char> stage;
+  for (int f = 0; f < M; ++f) {
+    const int64_t n = n_pts[f];
+    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr;
+    CU(cudaMalloc(&d_o, rec * n)); c->frame_allocs.push_back(d_o);
+    CU(cudaMalloc(&d_s, rec * n)); c->frame_allocs.push_back(d_s);
+    CU(cudaMalloc(&d_b, sizeof(Box) * builds[f].boxes.size())); c->frame_allocs.push_back(d_b);
+    stage.resize(rec * n);
+    pack_records(f32, pts[f], nullptr, nullptr, n, stage.data());
+    CU(cudaMemcpy(d_o, stage.data(), rec * n, cudaMemcpyHostToDevice));
+    pack_records(f32, pts[f], builds[f].order.data(), builds[f].order.data(), n, stage.data());
+    CU(cudaMemcpy(d_s, stage.data(), rec * n, cudaMemcpyHostToDevice));
+    if (nor && nor[f]) {
+      CU(cudaMalloc(&d_n, rec * n)); c->frame_allocs.push_back(d_n);
+      pack_records(f32, nor[f], nullptr, nullptr, n, stage.data());
+      CU(cudaMemcpy(d_n, stage.data(), rec * n, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(d_b, builds[f].boxes.data(), sizeof(Box) * builds[f].boxes.size(), cudaMemcpyHostToDevice));
+    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const Box*)d_b, (int32_t)n, builds[f].n_leaf_pad};
+  }
+  RET(c->d_frames.reserve(sizeof(FrameDev) * M));
+  CU(cudaMemcpy(c->d_frames.p, c->h_frames.data(), sizeof(FrameDev) * M, cudaMemcpyHostToDevice));
+  RET(c->d_poses.reserve(sizeof(double) * 16 * M));
+  c->h_poses.assign((size_t)16 * M, 0.0);
+  for (int f = 0; f < M; ++f) for (int i = 0; i < 4; ++i) c->h_poses[16 * f + 5 * i] = 1.0;
+  CU(cudaMemcpy(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * M, cudaMemcpyHostToDevice));
+  c->fixed.assign(M, 0); c->fixed[0] = 1;
+  c->E = 0; c->h_edges.clear(); c->have_corr = false;
+  return MVICP_OK;
+}
+
+int mvicp_set_poses(mvicp_ctx* c, const double* poses16, const uint8_t* fixed) {
+  if (!c || !c->M || !poses16) return fail(MVICP_ERR_INVALID, "mvicp_set_poses: bad arguments / no frames");
+  CU(cudaSetDevice(c->device));
+  std::memcpy(c->h_poses.data(), poses16, sizeof(double) * 16 * c->M);
+  CU(cudaMemcpyAsync(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * c->M, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (fixed) c->fixed.assign(fixed, fixed + c->M);
+  return MVICP_OK;
+}
+
+int mvicp_get_poses(mvicp_ctx* c, double* poses16) {
+  if (!c || !c->M || !poses16) return fail(MVICP_ERR_INVALID, "mvicp_get_poses: bad arguments / no frames");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->h_poses.data(), c->d_poses.p, sizeof(double) * 16 * c->M, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::memcpy(poses16, c->h_poses.data(), sizeof(double) * 16 * c->M);
+  return MVICP_OK;
+}
+
+// (re)build tile lists and per-edge buffers; called by set_graph and comm_init
+static int rebuild_work(mvicp_ctx* c) {
+  const int E = c->E;
+  if (!E) return MVICP_OK;
+  int64_t off = 0, owned_slots = 0;
+  for (int e = 0; e < E; ++e) {
+    EdgeDev& ed = c->h_edges[e];
+    ed.off = off; ed.n_src = (int32_t)c->n_pts[ed.src];
+    ed.owned = (owner_of(c, ed.src) == c->rank && !c->fixed[ed.src]) ? 1 : 0;   // fixed src: `if(this->fixed) return;` frame.cpp:93
+    off += ed.n_src;
+    if (ed.owned) owned_slots += ed.n_src;
+  }
+  c->total_slots = off;
+  // LM streaming tile: long enough to amortise the 28-value block reduction, short enough to fill 148 SMs
+  int tl = 8192;
+  while (tl > 1024 && owned_slots / tl < 4 * 148) tl >>= 1;
+  c->eval_tile_len = tl;
+  std::vector<Tile> kt, et; std::vector<int32_t> etb(E + 1, 0);
+  for (int e = 0; e < E; ++e) {
+    const EdgeDev& ed = c->h_edges[e];
+    etb[e] = (int32_t)et.size();
+    if (!ed.owned) continue;
+    for (int s = 0; s < ed.n_src; s += KNN_TILE) kt.push_back(Tile{e, s});
+    for (int s = 0; s < ed.n_src; s += tl) et.push_back(Tile{e, s});
+  }
+  etb[E] = (int32_t)et.size();
+  c->n_knn_tiles = (int)kt.size(); c->n_eval_tiles = (int)et.size();
+  RET(c->d_edges.reserve(sizeof(EdgeDev) * E));
+  RET(c->d_xf.reserve(sizeof(EdgeXf) * E));
+  RET(c->d_corr.reserve(sizeof(int32_t) * off));
+  RET(c->d_d2.reserve(sizeof(double) * off));
+  RET(c->d_count.reserve(sizeof(unsigned long long) * E));
+  RET(c->d_sel.reserve(sizeof(SelState) * E));
+  RET(c->d_hist.reserve(sizeof(unsigned int) * SEL_BINS * (size_t)E));
+  RET(c->d_weight.reserve(sizeof(float) * E));
+  RET(c->d_median.reserve(sizeof(double) * E));
+  RET(c->d_knn_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, kt.size())));
+  RET(c->d_eval_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, et.size())));
+  RET(c->d_edge_tile_begin.reserve(sizeof(int32_t) * (E + 1)));
+  RET(c->d_partial.reserve(sizeof(double) * NBLK * std::max<size_t>(1, et.size())));
+  RET(c->d_blocks.reserve(sizeof(double) * NBLK * E));
+  CU(cudaMemcpy(c->d_edges.p, c->h_edges.data(), sizeof(EdgeDev) * E, cudaMemcpyHostToDevice));
+  if (!kt.empty()) CU(cudaMemcpy(c->d_knn_tiles.p, kt.data(), sizeof(Tile) * kt.size(), cudaMemcpyHostToDevice));
+  if (!et.empty()) CU(cudaMemcpy(c->d_eval_tiles.p, et.data(), sizeof(Tile) * et.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_edge_tile_begin.p, etb.data(), sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice));
+  CU(cudaMemset(c->d_hist.p, 0, sizeof(unsigned int) * SEL_BINS * (size_t)E));
+  CU(cudaMemset(c->d_weight.p, 0, sizeof(float) * E));
+  CU(cudaMemset(c->d_count.p, 0, sizeof(unsigned long long) * E));
+  CU(cudaMemset(c->d_corr.p, 0xff, sizeof(int32_t) * off));   // ~0 = "no inlier, candidate 0"
+  c->h_weight.assign(E, 0.f); c->h_count.assign(E, 0ull);
+  c->have_corr = false;
+  return MVICP_OK;
+}
+
+int mvicp_set_graph(mvicp_ctx* c, int32_t E, const int32_t* src, const int32_t* dst) {
+  if (!c || !c->M || E < 0 || (E && (!src || !dst))) return fail(MVICP_ERR_INVALID, "mvicp_set_graph: bad arguments / no frames");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int e = 0; e < E; ++e)
+    if (src[e] < 0 || src[e] >= c->M || dst[e] < 0 || dst[e] >= c->M || src[e] == dst[e])
+      return fail(MVICP_ERR_INVALID, "edge %d: (%d -> %d) invalid", e, src[e], dst[e]);
+  c->E = E; c->h_edges.assign(E, EdgeDev{});
+  for (int e = 0; e < E; ++e) { c->h_edges[e].src = src[e]; c->h_edges[e].dst = dst[e]; }
+  return rebuild_work(c);
+}
+
+int mvicp_pose_graph_knn(mvicp_ctx* c, int32_t knn) {
+  if (!c || !c->M || knn < 0) return fail(MVICP_ERR_INVALID, "mvicp_pose_graph_knn: bad arguments / no frames");
+  // Frame::computePoseNeighboursKnn (frame.cpp:67-89): k frames with the smallest float |t_i - t_j|
+  std::vector<int32_t> src, dst;
+  for (int i = 0; i < c->M; ++i) {
+    std::vector<std::pair<float, int>> nb;
+    for (int j = 0; j < c->M; ++j) {
+      if (i == j) continue;
+      const double* a = &c->h_poses[16 * i + 12]; const double* b = &c->h_poses[16 * j + 12];
+      const double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+      nb.push_back({(float)std::sqrt(d0 * d0 + d1 * d1 + d2 * d2), j});
+    }
+    std::stable_sort(nb.begin(), nb.end(), [](const std::pair<float, int>& x, const std::pair<float, int>& y) { return x.first < y.first; });
+    for (int q = 0; q < knn && q < (int)nb.size(); ++q) { src.push_back(i); dst.push_back(nb[q].second); }
+  }
+  return mvicp_set_graph(c, (int32_t)src.size(), src.data(), dst.data());
+}
+
+int mvicp_get_graph(mvicp_ctx* c, int32_t* E, int32_t* src, int32_t* dst) {
+  if (!c || !E) return fail(MVICP_ERR_INVALID, "mvicp_get_graph: bad arguments");
+  *E = c->E;
+  for (int e = 0; e < c->E; ++e) { if (src) src[e] = c->h_edges[e].src; if (dst) dst[e] = c->h_edges[e].dst; }
+  return MVICP_OK;
+}
+
+}  // extern "C"
+template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
+  const int E = c->E;
+  edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
+  CU(cudaMemsetAsync(c->d_count.p, 0, sizeof(unsigned long long) * E, c->stream));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
+  if (c->n_knn_tiles)
+    knn_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
+        c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
+        c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr,
+        c->d_count.as<unsigned long long>(), (double)thresh);
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);
+  // exact median -> weight
+  select_init_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_count.as<unsigned long long>(), c->d_sel.as<SelState>(), E);
+  c->stats.kernel_launches += 1;
+  const int shifts[6] = {53, 42, 31, 20, 9, 0}, nbits[6] = {11, 11, 11, 11, 11, 9};
+  for (int p = 0; p < 6; ++p) {
+    if (c->n_eval_tiles)
+      select_hist_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(
+          c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len, c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
+          c->d_sel.as<SelState>(), shifts[p], nbits[p], c->d_hist.as<unsigned int>());
+    select_pick_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_hist.as<unsigned int>(), shifts[p], p == 5,
+                                                         c->d_weight.as<float>(), c->d_median.as<double>());
+    c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
+  }
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  CU(cudaGetLastError());
+  return MVICP_OK;
+}
+
+extern "C" {
+int mvicp_correspond(mvicp_ctx* c, float thresh) {
+  if (!c || !c->M || !c->E) return fail(MVICP_ERR_STATE, "mvicp_correspond: frames and graph must be set first");
+  CU(cudaSetDevice(c->device));
+  RET(c->f32 ? launch_correspond<true>(c, thresh) : launch_correspond<false>(c, thresh));
+  c->have_corr = true; c->ev_knn = true;
+  int64_t q = 0; for (const EdgeDev& e : c->h_edges) if (e.owned) q += e.n_src;
+  c->stats.queries = q;
+  return MVICP_OK;
+}
+
+static int fetch_edge_meta(mvicp_ctx* c) {
+  CU(cudaMemcpyAsync(c->h_weight.data(), c->d_weight.p, sizeof(float) * c->E, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_count.data(), c->d_count.p, sizeof(unsigned long long) * c->E, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return MVICP_OK;
+}
+
+int mvicp_get_edge(mvicp_ctx* c, int32_t e, int32_t* first, int32_t* second, double* dist, int64_t* count, float* weight) {
+  if (!c || e < 0 || e >= c->E) return fail(MVICP_ERR_INVALID, "mvicp_get_edge: bad edge");
+  CU(cudaSetDevice(c->device));
+  const EdgeDev& ed = c->h_edges[e];
+  if (!ed.owned && !c->fixed[ed.src]) return fail(MVICP_ERR_NOT_OWNER, "edge %d is processed by rank %d", e, owner_of(c, ed.src));
+  RET(fetch_edge_meta(c));
+  if (weight) *weight = c->h_weight[e];
+  if (count) *count = (int64_t)c->h_count[e];
+  if (first || second || dist) {
+    std::vector<int32_t> corr(ed.n_src); std::vector<double> d2(ed.n_src);
+    CU(cudaMemcpy(corr.data(), c->d_corr.as<int32_t>() + ed.off, sizeof(int32_t) * ed.n_src, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(d2.data(), c->d_d2.as<double>() + ed.off, sizeof(double) * ed.n_src, cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    for (int k = 0; k < ed.n_src; ++k)
+      if (corr[k] >= 0) {
+        if (first) first[n] = k;
+        if (second) second[n] = corr[k];
+        if (dist) dist[n] = std::sqrt(d2[k]);
+        ++n;
+      }
+    if (count) *count = n;
+  }
+  return MVICP_OK;
+}
+
+int mvicp_get_nn(mvicp_ctx* c, int32_t e, int32_t* nn_idx, double* nn_d2) {
+  if (!c || e < 0 || e >= c->E) return fail(MVICP_ERR_INVALID, "mvicp_get_nn: bad edge");
+  CU(cudaSetDevice(c->device));
+  const EdgeDev& ed = c->h_edges[e];
+  if (!ed.owned) return fail(MVICP_ERR_NOT_OWNER, "edge %d is not processed by this rank", e);
+  CU(cudaStreamSynchronize(c->stream));
+  if (nn_idx) {
+    CU(cudaMemcpy(nn_idx, c->d_corr.as<int32_t>() + ed.off, sizeof(int32_t) * ed.n_src, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < ed.n_src; ++k) if (nn_idx[k] < 0) nn_idx[k] = ~nn_idx[k];
+  }
+  if (nn_d2) CU(cudaMemcpy(nn_d2, c->d_d2.as<double>() + ed.off, sizeof(double) * ed.n_src, cudaMemcpyDeviceToHost));
+  return MVICP_OK;
+}
+
+int mvicp_set_edge(mvicp_ctx* c, int32_t e, const int32_t* first, const int32_t* second, int64_t count, float weight) {
+  if (!c || e < 0 || e >= c->E || count < 0 || (count && (!first || !second))) return fail(MVICP_ERR_INVALID, "mvicp_set_edge: bad arguments");
+  CU(cudaSetDevice(c->device));
+  const EdgeDev& ed = c->h_edges[e];
+  std::vector<int32_t> corr(ed.n_src, ~0);
+  const int n_dst = (int)c->n_pts[ed.dst];
+  for (int64_t i = 0; i < count; ++i) {
+    if (first[i] < 0 || first[i] >= ed.n_src || second[i] < 0 || second[i] >= n_dst) return fail(MVICP_ERR_INVALID, "mvicp_set_edge: index out of range at %lld", (long long)i);
+    corr[first[i]] = second[i];
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(c->d_corr.as<int32_t>() + ed.off, corr.data(), sizeof(int32_t) * ed.n_src, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_weight.as<float>() + e, &weight, sizeof(float), cudaMemcpyHostToDevice));
+  const unsigned long long cnt = (unsigned long long)count;
+  CU(cudaMemcpy(c->d_count.as<unsigned long long>() + e, &cnt, sizeof cnt, cudaMemcpyHostToDevice));
+  return MVICP_OK;
+}
+
+int mvicp_closest_point(mvicp_ctx* c, int32_t frame, const double q[3], int64_t* idx, double* d2) {
+  if (!c || frame < 0 || frame >= c->M || !q) return fail(MVICP_ERR_INVALID, "mvicp_closest_point: bad arguments");
+  CU(cudaSetDevice(c->device));
+  long long* d_i; double* d_d;
+  CU(cudaMalloc(&d_i, 8)); CU(cudaMalloc(&d_d, 8));
+  if (c->f32) knn_single_kernel<true><<<1, 1, 0, c->stream>>>(c->d_frames.as<FrameDev>(), frame, q[0], q[1], q[2], d_i, d_d);
+  else knn_single_kernel<false><<<1, 1, 0, c->stream>>>(c->d_frames.as<FrameDev>(), frame, q[0], q[1], q[2], d_i, d_d);
+  c->stats.kernel_launches += 1;
+  long long hi = 0; double hd = 0;
+  CU(cudaMemcpyAsync(&hi, d_i, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&hd, d_d, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_i); cudaFree(d_d);
+  if (idx) *idx = hi;
+  if (d2) *d2 = hd;
+  return MVICP_OK;
+}
+
+// ---- LM ------------------------------------------------------------------------------------------
+static int prepare_lm(mvicp_ctx* c, int n) {
+  const int M = c->M, E = c->E;
+  RET(c->d_state.reserve(sizeof(LmState)));
+  RET(c->d_x.reserve(sizeof(double) * 7 * M)); RET(c->d_cand.reserve(sizeof(double) * 7 * M));
+  RET(c->d_Rt.reserve(sizeof(Rt) * M)); RET(c->d_K.reserve(sizeof(double) * 36 * M));
+  RET(c->d_col.reserve(sizeof(int32_t) * M));
+  RET(c->d_H.reserve(sizeof(double) * n * n)); RET(c->d_Hc.reserve(sizeof(double) * n * n)); RET(c->d_L.reserve(sizeof(double) * n * n));
+  RET(c->d_g.reserve(sizeof(double) * n)); RET(c->d_gc.reserve(sizeof(double) * n)); RET(c->d_scale.reserve(sizeof(double) * n));
+  RET(c->d_diag.reserve(sizeof(double) * n)); RET(c->d_rhs.reserve(sizeof(double) * n)); RET(c->d_step.reserve(sizeof(double) * n));
+  RET(c->d_Bs.reserve(sizeof(double) * 72 * E)); RET(c->d_ABs.reserve(sizeof(double) * 72 * E));
+  RET(c->d_Hp.reserve(sizeof(double) * 144 * E)); RET(c->d_gp.reserve(sizeof(double) * 12 * E));
+  return MVICP_OK;
+}
+
+}  // extern "C"
+template <bool F32> static void launch_eval(mvicp_ctx* c, int cost, int robust) {
+  const int nt = c->n_eval_tiles;
+  if (!nt) return;
+#define MV_EVAL(COSTK)                                                                                           \
+  lm_eval_kernel<F32, COSTK><<<nt, EVAL_THREADS, 0, c->stream>>>(                                                \
+      c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
+      c->d_corr.as<int32_t>(), c->d_Rt.as<Rt>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>())
+  if (cost == COST_P2P) MV_EVAL(COST_P2P); else if (cost == COST_P2PLANE) MV_EVAL(COST_P2PLANE); else MV_EVAL(COST_MIXED);
+#undef MV_EVAL
+}
+
+extern "C" {
+int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, const mvicp_lm_options* opt_in, mvicp_lm_summary* summary) {
+  if (!c || !c->M || !c->E) return fail(MVICP_ERR_STATE, "mvicp_optimize: frames and graph must be set first");
+  if (param < 0 || param > 2 || cost < 0 || cost > 2) return fail(MVICP_ERR_INVALID, "mvicp_optimize: bad param/cost");
+  if (cost != COST_P2P && !c->have_normals) return fail(MVICP_ERR_INVALID, "point-to-plane needs normals for every frame");
+  CU(cudaSetDevice(c->device));
+  const int M = c->M, E = c->E;
+  c->fixed[0] = 1;   // frames[0]->fixed = true (icp-ceres.cpp:242-244,342-344,417-419)
+  // local columns of the free frames; edges of fixed src frames contribute nothing (icp-ceres.cpp:255,353,426)
+  c->h_col.assign(M, -1); int n = 0;
+  for (int f = 0; f < M; ++f) if (!c->fixed[f]) { c->h_col[f] = n; n += 6; }
+  c->n_free = n / 6;
+  mvicp_lm_options opt; if (opt_in) opt = *opt_in; else mvicp_default_lm_options(&opt);
+  if (n == 0) {   // nothing to optimise; still "writes the poses back"
+    if (summary) { std::memset(summary, 0, sizeof *summary); summary->termination = MVICP_TERM_GRADIENT_TOLERANCE; }
+    return MVICP_OK;
+  }
+  // ownership may depend on `fixed`: refresh the edge table if it changed
+  bool stale = false;
+  for (int e = 0; e < E; ++e) {
+    const int want = (owner_of(c, c->h_edges[e].src) == c->rank && !c->fixed[c->h_edges[e].src]) ? 1 : 0;
+    if (want != c->h_edges[e].owned) stale = true;
+  }
+  if (stale) return fail(MVICP_ERR_STATE, "fixed flags changed after mvicp_set_graph: call mvicp_set_graph again");
+  RET(prepare_lm(c, n));
+  // block-sparse gather lists
+  std::vector<std::vector<std::pair<int, int>>> blk((size_t)M * M);
+  std::vector<std::vector<std::pair<int, int>>> gl(M);
+  for (int e = 0; e < E; ++e) {
+    const int s = c->h_edges[e].src, k = c->h_edges[e].dst;
+    if (c->fixed[s]) continue;
+    blk[(size_t)s * M + s].push_back({e, 0}); gl[s].push_back({e, 0});
+    if (!c->fixed[k]) {
+      blk[(size_t)s * M + k].push_back({e, 1}); blk[(size_t)k * M + s].push_back({e, 2}); blk[(size_t)k * M + k].push_back({e, 3});
+      gl[k].push_back({e, 1});
+    }
+  }
+  std::vector<int32_t> hb_ptr{0}, hb_row, hb_col, hc_edge, hc_sub, gb_ptr{0}, gc_edge, gc_side;
+  for (int r = 0; r < M; ++r)
+    for (int q = 0; q < M; ++q) {
+      const auto& l = blk[(size_t)r * M + q];
+      if (l.empty()) continue;
+      hb_row.push_back(c->h_col[r]); hb_col.push_back(c->h_col[q]);
+      for (auto& pr : l) { hc_edge.push_back(pr.first); hc_sub.push_back(pr.second); }
+      hb_ptr.push_back((int32_t)hc_edge.size());
+    }
+  for (int f = 0; f < M; ++f) { for (auto& pr : gl[f]) { gc_edge.push_back(pr.first); gc_side.push_back(pr.second); } gb_ptr.push_back((int32_t)gc_edge.size()); }
+  c->n_hblocks = (int)hb_row.size();
+  auto up = [&](DevBuf& b, const std::vector<int32_t>& v) -> int {
+    RET(b.reserve(sizeof(int32_t) * std::max<size_t>(1, v.size())));
+    if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, c->stream));
+    return MVICP_OK;
+  };
+  RET(up(c->d_hb_ptr, hb_ptr)); RET(up(c->d_hb_row, hb_row)); RET(up(c->d_hb_col, hb_col)); RET(up(c->d_hc_edge, hc_edge));
+  RET(up(c->d_hc_sub, hc_sub)); RET(up(c->d_gb_ptr, gb_ptr)); RET(up(c->d_gc_edge, gc_edge)); RET(up(c->d_gc_side, gc_side));
+  RET(up(c->d_col, c->h_col));
+
+  LmState st; std::memset(&st, 0, sizeof st);
+  st.opt = opt; st.param = param; st.cost_kind = cost; st.robust = robust ? 1 : 0; st.M = M; st.E = E; st.F = n / 6; st.n = n;
+  st.G = ambient_size(param); st.radius = opt.initial_trust_region_radius; st.decrease_factor = 2.0;
+  CU(cudaMemcpyAsync(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));   // host vectors above go out of scope only after the copies landed
+
+  LmWork w{};
+  w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.blocks = c->d_blocks.as<double>();
+  w.x = c->d_x.as<double>(); w.cand = c->d_cand.as<double>(); w.Rt_eval = c->d_Rt.as<Rt>(); w.K_eval = c->d_K.as<double>();
+  w.col = c->d_col.as<int32_t>();
+  w.hb_ptr = c->d_hb_ptr.as<int32_t>(); w.hb_row = c->d_hb_row.as<int32_t>(); w.hb_col = c->d_hb_col.as<int32_t>();
+  w.hc_edge = c->d_hc_edge.as<int32_t>(); w.hc_sub = c->d_hc_sub.as<int32_t>(); w.n_hblocks = c->n_hblocks;
+  w.gb_ptr = c->d_gb_ptr.as<int32_t>(); w.gc_edge = c->d_gc_edge.as<int32_t>(); w.gc_side = c->d_gc_side.as<int32_t>();
+  w.H = c->d_H.as<double>(); w.g = c->d_g.as<double>(); w.Hc = c->d_Hc.as<double>(); w.gc = c->d_gc.as<double>();
+  w.scale = c->d_scale.as<double>(); w.diag = c->d_diag.as<double>(); w.Lg = c->d_L.as<double>(); w.rhs = c->d_rhs.as<double>();
+  w.step = c->d_step.as<double>(); w.Bs = c->d_Bs.as<double>(); w.ABs = c->d_ABs.as<double>(); w.Hp = c->d_Hp.as<double>();
+  w.gp = c->d_gp.as<double>(); w.poses16 = c->d_poses.as<double>();
+  const size_t l_bytes = sizeof(double) * (size_t)n * n;
+  w.l_in_smem = l_bytes <= 200 * 1024 ? 1 : 0;
+  const size_t dyn = w.l_in_smem ? l_bytes : 0;
+  CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  lm_init_kernel<<<(M + 63) / 64, 64, 0, c->stream>>>(w);
+  c->stats.kernel_launches += 1;
+  int evals = 0;
+  const int max_evals = opt.max_num_iterations + 2;
+  while (true) {
+    if (c->f32) launch_eval<true>(c, cost, st.robust); else launch_eval<false>(c, cost, st.robust);
+    lm_reduce_kernel<<<E, 32, 0, c->stream>>>(c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(), c->d_blocks.as<double>());
+    if (c->comm && c->world > 1)
+      NC(ncclAllReduce(c->d_blocks.p, c->d_blocks.p, (size_t)NBLK * E, ncclDouble, ncclSum, c->comm, c->stream));
+    lm_step_kernel<<<1, STEP_THREADS, dyn, c->stream>>>(w);
+    c->stats.kernel_launches += (c->n_eval_tiles ? 1 : 0) + 2;
+    ++evals;
+    CU(cudaMemcpyAsync(c->h_done, &w.S->done, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (*c->h_done || evals > max_evals) break;
+  }
+  // sharded runs: every rank holds identical poses (identical solve on identical all-reduced blocks); the
+  // owners' copies are gathered anyway so that a caller never sees rank-dependent state.
+  if (c->comm && c->world > 1) {
+    const int chunk = (M + c->world - 1) / c->world;
+    RET(c->d_posegather.reserve(sizeof(double) * 16 * (size_t)chunk * c->world * 2));
+    double* sendb = c->d_posegather.as<double>();
+    double* recvb = sendb + (size_t)16 * chunk * c->world;
+    CU(cudaMemsetAsync(sendb, 0, sizeof(double) * 16 * chunk, c->stream));
+    int f0 = -1, f1 = -1;
+    for (int f = 0; f < M; ++f) if (owner_of(c, f) == c->rank) { if (f0 < 0) f0 = f; f1 = f; }
+    if (f0 >= 0) CU(cudaMemcpyAsync(sendb, c->d_poses.as<double>() + 16 * f0, sizeof(double) * 16 * (f1 - f0 + 1), cudaMemcpyDeviceToDevice, c->stream));
+    NC(ncclAllGather(sendb, recvb, (size_t)16 * chunk, ncclDouble, c->comm, c->stream));
+    for (int r = 0; r < c->world; ++r) {
+      int a = -1, b = -1;
+      for (int f = 0; f < M; ++f) if (owner_of(c, f) == r) { if (a < 0) a = f; b = f; }
+      if (a >= 0) CU(cudaMemcpyAsync(c->d_poses.as<double>() + 16 * a, recvb + (size_t)16 * chunk * r, sizeof(double) * 16 * (b - a + 1), cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  CU(cudaEventRecord(c->ev[4], c->stream));
+  CU(cudaMemcpyAsync(&st, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  c->ev_lm = true;
+  if (summary) {
+    summary->termination = st.termination; summary->num_iterations = st.iteration; summary->num_successful_steps = st.n_success;
+    summary->num_evaluations = st.n_evals; summary->num_linear_solves = st.n_solves; summary->reserved = 0;
+    summary->initial_cost = st.initial_cost; summary->final_cost = st.x_cost;
+  }
+  if (st.nonrigid)
+    return fail(MVICP_ERR_NONRIGID, "a pose's quaternion is not unit (non-rigid Isometry): the unit-quaternion LM path was run; "
+                                    "results differ from the reference's non-unit-quaternion arithmetic");
+  if (!st.done) return fail(MVICP_ERR_STATE, "LM loop did not terminate within %d evaluations", max_evals);
+  return MVICP_OK;
+}
+
+int mvicp_icp_round(mvicp_ctx* c, float thresh, int32_t param, int32_t cost, int32_t robust, const mvicp_lm_options* opt, mvicp_lm_summary* summary) {
+  RET(mvicp_correspond(c, thresh));
+  return mvicp_optimize(c, param, cost, robust, opt, summary);
+}
+
+int mvicp_pairwise(const mvicp_config* cfg, int32_t param, int32_t cost, const double* src, const double* dst, const double* nor,
+                   int64_t n, const mvicp_lm_options* opt, double* pose16_out, mvicp_lm_summary* summary) {
+  if (!src || !dst || n <= 0 || !pose16_out) return fail(MVICP_ERR_INVALID, "mvicp_pairwise: bad arguments");
+  if (cost != MVICP_COST_P2P && !nor) return fail(MVICP_ERR_INVALID, "mvicp_pairwise: point-to-plane needs dst normals");
+  mvicp_ctx* c = nullptr;
+  RET(mvicp_create(cfg, &c));
+  // frame 0 = dst (constant, identity), frame 1 = src (starts at identity); edge 1 -> 0 with identity matches
+  const double* pts[2] = {dst, src}; const double* nrs[2] = {nor, nor};   // src normals are never read
+  const int64_t np[2] = {n, n};
+  int rc = mvicp_set_frames(c, 2, pts, nor ? nrs : nullptr, np);
+  const int32_t es = 1, ed = 0;
+  if (rc == MVICP_OK) rc = mvicp_set_graph(c, 1, &es, &ed);
+  if (rc == MVICP_OK) {
+    std::vector<int32_t> id(n); std::iota(id.begin(), id.end(), 0);
+    rc = mvicp_set_edge(c, 0, id.data(), id.data(), n, 1.0f);
+  }
+  if (rc == MVICP_OK) rc = mvicp_optimize(c, param, cost, 0, opt, summary);
+  std::vector<double> poses(32);
+  if (rc == MVICP_OK) rc = mvicp_get_poses(c, poses.data());
+  if (rc == MVICP_OK) std::memcpy(pose16_out, poses.data() + 16, sizeof(double) * 16);
+  const std::string keep = g_err;
+  mvicp_destroy(c);
+  g_err = keep;
+  return rc;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------
+int mvicp_nccl_unique_id(void* out128) {
+  if (!out128) return fail(MVICP_ERR_INVALID, "mvicp_nccl_unique_id: null");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id; NC(ncclGetUniqueId(&id));
+  std::memcpy(out128, &id, 128);
+  return MVICP_OK;
+}
+
+int mvicp_comm_init(mvicp_ctx* c, const void* id128, int32_t rank, int32_t world) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(MVICP_ERR_INVALID, "mvicp_comm_init: bad arguments");
+  CU(cudaSetDevice(c->device));
+  if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
+  ncclUniqueId id; std::memcpy(&id, id128, 128);
+  if (world > 1) NC(ncclCommInitRank(&c->comm, world, id, rank));
+  c->rank = rank; c->world = world;
+  return rebuild_work(c);
+}
+
+// ---- introspection -------------------------------------------------------------------------------------
+int mvicp_get_stats(mvicp_ctx* c, mvicp_stats* out) {
+  if (!c || !out) return fail(MVICP_ERR_INVALID, "mvicp_get_stats: bad arguments");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->ev_knn) {
+    cudaEventElapsedTime(&c->stats.knn_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->stats.select_ms, c->ev[1], c->ev[2]);
+    c->stats.correspond_ms = c->stats.knn_ms + c->stats.select_ms;
+  }
+  if (c->ev_lm) cudaEventElapsedTime(&c->stats.optimize_ms, c->ev[3], c->ev[4]);
+  if (c->E && fetch_edge_meta(c) == MVICP_OK) {
+    int64_t s = 0; for (int e = 0; e < c->E; ++e) if (c->h_edges[e].owned) s += (int64_t)c->h_count[e];
+    c->stats.correspondences = s;
+  }
+  *out = c->stats;
+  return MVICP_OK;
+}
+int mvicp_get_stream(mvicp_ctx* c, void** stream) { if (!c || !stream) return fail(MVICP_ERR_INVALID, "bad arguments"); *stream = (void*)c->stream; return MVICP_OK; }
+int mvicp_sync(mvicp_ctx* c) { if (!c) return fail(MVICP_ERR_INVALID, "null ctx"); CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); return MVICP_OK; }
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// select.cuh -- exact per-edge median of the inlier distances -> OutgoingEdge::weight.
+//
+// Reference: std::nth_element(dists.begin(), dists.begin() + size/2, dists.end()); weight = nth * 1.5 narrowed
+// to float (src/internal/frame.cpp:166-176).  dists = sqrt(d2) and sqrt is monotone, so the element at sorted
+// position size/2 of the distances is the sqrt of the element at that position of the squared distances.
+// Non-negative doubles order like their bit patterns => an MSB-first radix select over the 64-bit patterns
+// gives the exact order statistic (6 passes of 11/11/11/11/11/9 bits, shared-memory histograms).
+#pragma once
+#include <cuda_runtime.h>
+#include "types.cuh"
+
+namespace mv {
+
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_THREADS = 256;
+
+struct SelState {            // one per edge
+  unsigned long long prefix; // bits decided so far (high part)
+  unsigned long long rank;   // remaining rank inside the current prefix bucket
+  unsigned long long count;  // inliers of the edge
+};
+
+__global__ void select_init_kernel(const unsigned long long* __restrict__ edge_count, SelState* __restrict__ st, int n_edges) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  st[e].prefix = 0ull; st[e].count = edge_count[e]; st[e].rank = edge_count[e] / 2;   // dists.size() / 2
+}
+
+// hist[e][bin] += #inliers of the tile whose high bits equal the edge's prefix and whose digit is `bin`
+__global__ void __launch_bounds__(SEL_THREADS)
+select_hist_kernel(const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles, int tile_len,
+                   const int32_t* __restrict__ corr, const double* __restrict__ d2, const SelState* __restrict__ st,
+                   int shift, int bits, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[SEL_BINS];
+  for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const Tile t = tiles[blockIdx.x];
+  const EdgeDev e = edges[t.edge];
+  const unsigned long long prefix = st[t.edge].prefix;
+  const int hi = shift + bits;
+  const unsigned int mask = (1u << bits) - 1u;
+  const int end = min(t.start + tile_len, e.n_src);
+  for (int k = t.start + threadIdx.x; k < end; k += blockDim.x) {
+    if (corr[e.off + k] < 0) continue;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(d2[e.off + k]);
+    if (hi < 64 && (key >> hi) != (prefix >> hi)) continue;
+    atomicAdd(&sh[(unsigned int)(key >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  unsigned int* h = hist + (size_t)t.edge * SEL_BINS;
+  for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
+// one block per edge: find the bin holding the wanted rank, extend the prefix, clear the histogram.
+// On the last pass the prefix is the exact bit pattern of the median squared distance -> weight.
+__global__ void __launch_bounds__(SEL_THREADS)
+select_pick_kernel(SelState* __restrict__ st, unsigned int* __restrict__ hist, int shift, int last,
+                   float* __restrict__ weight, double* __restrict__ median) {
+  const int e = blockIdx.x;
+  unsigned int* h = hist + (size_t)e * SEL_BINS;
+  __shared__ unsigned int part[SEL_THREADS];
+  __shared__ int s_bin; __shared__ unsigned long long s_before;
+  constexpr int PER = SEL_BINS / SEL_THREADS;
+  unsigned int loc[PER]; unsigned int sum = 0;
+  for (int i = 0; i < PER; ++i) { loc[i] = h[threadIdx.x * PER + i]; sum += loc[i]; }
+  part[threadIdx.x] = sum;
+  if (threadIdx.x == 0) { s_bin = -1; s_before = 0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // 256 partial sums: serial scan is fine (once per edge per pass)
+    unsigned long long acc = 0; const unsigned long long rank = st[e].rank;
+    for (int t = 0; t < SEL_THREADS; ++t) {
+      if (rank < acc + part[t]) { s_bin = t; s_before = acc; break; }
+      acc += part[t];
+    }
+  }
+  __syncthreads();
+  if (s_bin == (int)threadIdx.x) {
+    unsigned long long acc = s_before; const unsigned long long rank = st[e].rank;
+    for (int i = 0; i < PER; ++i) {
+      if (rank < acc + loc[i]) {
+        st[e].prefix |= ((unsigned long long)(threadIdx.x * PER + i)) << shift;
+        st[e].rank = rank - acc;
+        break;
+      }
+      acc += loc[i];
+    }
+  }
+  for (int i = 0; i < PER; ++i) h[threadIdx.x * PER + i] = 0u;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    if (st[e].count == 0) { weight[e] = 0.0f; median[e] = __longlong_as_double(0x7ff8000000000000LL); }
+    else {
+      const double nth = __dsqrt_rn(__longlong_as_double((long long)st[e].prefix));
+      median[e] = nth;
+      weight[e] = __double2float_rn(__dmul_rn(nth, 1.5));
+    }
+  }
+}
+
+}  // namespace mv

@@ -1,0 +1,47 @@
+// types.cuh -- device-visible data layout of the engine.
+//
+// HBM layout.  Every frame keeps, resident for the life of the context:
+//   pts_o / nor_o : points / normals in the caller's order, one 16-byte (float4) or 32-byte (double4)
+//                   record each -> the LM kernel's coalesced src stream and its dst gathers;
+//   pts_s         : the same points in Morton order, record.w = original index -> NN search leaves;
+//   boxes         : implicit binary AABB tree over leaves of LEAF consecutive Morton-sorted points,
+//                   heap order (root = 1, children 2i, 2i+1, leaves at [n_leaf_pad, 2 n_leaf_pad)).
+// float storage is used iff every coordinate of every frame is exactly fp32-representable
+// (checked at upload); arithmetic is fp64 either way, so results do not depend on the choice.
+#pragma once
+#include <stdint.h>
+
+namespace mv {
+
+constexpr int LEAF = 8;          // points per BVH leaf
+constexpr int KNN_TILE = 256;    // queries per CTA of the NN kernel
+constexpr int EVAL_TILE = 2048;  // correspondence slots per CTA of the LM streaming kernel
+constexpr int EVAL_THREADS = 256;
+constexpr int NBLK = 28;         // per-edge block: 21 (upper 6x6) + 6 (rhs) + 1 (cost)
+
+struct Box { float lo[3]; float hi[3]; float pad[2]; };   // 32 B; child pairs are 64-B contiguous
+
+struct double4a { double x, y, z, w; };   // 32-byte record for the fp64 storage mode
+
+struct FrameDev {
+  const void* pts_o;     // float4* or double4a*
+  const void* nor_o;     // may be null
+  const void* pts_s;     // Morton order, .w = original index (int bits / int64 bits)
+  const Box* boxes;      // 2 * n_leaf_pad entries (entry 0 unused)
+  int32_t n;             // points
+  int32_t n_leaf_pad;    // power of two >= ceil(n / LEAF)
+};
+
+struct EdgeDev {
+  int32_t src, dst;
+  int64_t off;           // offset of this edge's slot 0 in the flat per-query arrays
+  int32_t n_src;
+  int32_t owned;         // 1 if this rank processes the edge
+};
+
+// Per-edge constants of the query transform (frame.cpp:117-118,131,136), recomputed from the poses.
+struct EdgeXf { double Rs[9], ts[3], Rinv[9], td[3]; };
+
+struct Tile { int32_t edge; int32_t start; };   // work item: `count` slots of one edge from `start`
+
+}  // namespace mv

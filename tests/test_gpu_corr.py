@@ -1,0 +1,148 @@
+"""GPU parity of the correspondence step (mvicp_correspond) against the CPU oracle, through the C ABI.
+Bar: nearest-neighbour indices and squared distances bit-exact, inlier lists identical, float weight bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import oracle_correspond, scene
+from mv_lm_icp_b200 import Engine, synth
+from mv_lm_icp_b200.api import FLAG_NO_SEED
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_edges(eng, ref, edges):
+    ties = 0
+    for e, (s, d) in enumerate(edges):
+        if ref[e] is None:
+            cnt, w = eng.get_edge(e, arrays=False)
+            assert cnt == 0
+            continue
+        idx, d2 = eng.get_nn(e)
+        r = ref[e]
+        assert np.array_equal(d2.view(np.uint64), r["nn_d2"].view(np.uint64)), f"edge {e}: d2 not bit-exact"
+        diff = idx != r["nn_idx"]
+        ties += int(diff.sum())   # equal d2 but different index = exact tie (tie rule differs only vs nanoflann)
+        assert not diff.any(), f"edge {e}: {diff.sum()} index mismatches"
+        f, sec, dist, w = eng.get_edge(e)
+        assert np.array_equal(f, r["first"]) and np.array_equal(sec, r["second"])
+        assert np.array_equal(dist.view(np.uint64), r["dist"].view(np.uint64))
+        assert np.float32(w).view(np.uint32) == np.float32(r["weight"]).view(np.uint32), (w, r["weight"])
+    return ties
+
+
+@pytest.mark.parametrize("n_views,n_points,cfg", [(4, 5000, 21), (6, 20011, 22)])
+def test_synthetic_bit_exact(oracle, n_views, n_points, cfg):
+    sc = scene(n_views, n_points, cfg)
+    edges = synth.ring_edges(n_views, 2)
+    eng = Engine()
+    eng.set_frames(sc["pts"], sc["nor"])
+    eng.set_graph(edges)
+    for poses in (sc["poses_init"], sc["poses_gt"]):   # far and near queries; second call is seeded by the first
+        eng.set_poses(poses)
+        eng.correspond(0.05)
+        ref = oracle_correspond(oracle, sc["pts"], poses, edges)
+        _check_edges(eng, ref, edges)
+    eng.close()
+
+
+def test_seed_does_not_change_results(oracle):
+    sc = scene(4, 5000, 21)
+    edges = synth.ring_edges(4, 2)
+    res = []
+    for flags in (0, FLAG_NO_SEED):
+        eng = Engine(flags=flags)
+        eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges)
+        for poses in (sc["poses_init"], sc["poses_gt"], sc["poses_init"]):
+            eng.set_poses(poses); eng.correspond(0.05)
+        res.append([eng.get_nn(e) for e in range(len(edges)) if edges[e][0] != 0])
+        eng.close()
+    for (i0, d0), (i1, d1) in zip(*res):
+        assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
+
+
+def test_real_bunny_pair_fp64_storage(oracle, golden_dir):
+    """Config 1: real scans (not fp32-representable -> fp64 storage path), non-rigid sample poses, general inverse.
+    Golden answer = the reference's own nanoflann (tests/golden/make_golden.py)."""
+    g = np.load(f"{golden_dir}/bunny_pair.npz")
+    eng = Engine()
+    eng.set_frames([g["pts0"], g["pts1"]], [g["nor0"], g["nor1"]])
+    eng.set_graph([(1, 0)])
+    eng.set_poses([g["pose0"], g["pose1"]])
+    eng.correspond(0.05)
+    idx, d2 = eng.get_nn(0)
+    assert np.array_equal(d2.view(np.uint64), g["nn_d2"].view(np.uint64))
+    assert np.array_equal(idx, g["nn_idx"])
+    f, s, dist, w = eng.get_edge(0)
+    assert np.array_equal(f, g["first"]) and np.array_equal(s, g["second"])
+    assert np.array_equal(dist.view(np.uint64), g["dist"].view(np.uint64))
+    assert np.float32(w).view(np.uint32) == np.float32(g["weight"]).view(np.uint32)
+    eng.close()
+
+
+def test_edge_cases(oracle):
+    rng = np.random.default_rng(5)
+    # tiny clouds (1, 7, 9 points: below / around one leaf), ragged sizes, a frame far away (all outliers)
+    pts = [rng.normal(size=(n, 3)).astype(np.float32).astype(np.float64) * 0.01 for n in (1, 7, 9, 300)]
+    pts.append(pts[3][:50] + 10.0)
+    pts[4] = pts[4].astype(np.float32).astype(np.float64)
+    poses = [np.eye(4) for _ in pts]
+    edges = [(1, 0), (2, 1), (3, 2), (1, 3), (4, 3), (3, 4), (2, 0)]
+    eng = Engine()
+    eng.set_frames(pts, None)
+    eng.set_graph(edges); eng.set_poses(poses)
+    eng.correspond(0.05)
+    ref = oracle_correspond(oracle, pts, poses, edges, kind="brute")
+    _check_edges(eng, ref, edges)
+    cnt, w = eng.get_edge(4, arrays=False)   # frame 4 is 10 m away: no inliers; oracle choice weight = 0
+    assert cnt == 0 and w == 0.0
+    # exact duplicates in the dst cloud: tie -> lowest index, same as the brute-force oracle
+    dup = np.repeat(pts[3][:20], 2, axis=0)
+    eng2 = Engine(); eng2.set_frames([dup, pts[3]], None); eng2.set_graph([(1, 0)]); eng2.set_poses([np.eye(4)] * 2)
+    eng2.correspond(0.05)
+    ref2 = oracle_correspond(oracle, [dup, pts[3]], [np.eye(4)] * 2, [(1, 0)], kind="brute")
+    _check_edges(eng2, ref2, [(1, 0)])
+    eng.close(); eng2.close()
+
+
+def test_closest_point_api(oracle):
+    sc = scene(4, 5000, 21)
+    eng = Engine(); eng.set_frames(sc["pts"], sc["nor"])
+    kd = oracle.KdIndex(sc["pts"][2], "kd")
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        q = sc["pts"][2][rng.integers(5000)] + rng.normal(0, 0.003, 3)
+        i, d2 = eng.closest_point(2, q)
+        ri, rd = kd.closest_points(q[None], np.eye(4), np.eye(4))
+        assert i == ri[0] and d2 == rd[0]
+    eng.close()
+
+
+def test_full_size_properties(oracle):
+    """BASELINE config 3 shape (20 x 200k): size-independent checks + oracle on a sample of queries."""
+    M, N = 20, 200_000
+    sc = scene(M, N, 3)
+    edges = synth.ring_edges(M, 2)
+    eng = Engine(); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
+    eng.correspond(0.05)
+    rng = np.random.default_rng(0)
+    for e in rng.choice(len(edges), 4, replace=False):
+        s, d = edges[e]
+        if s == 0:
+            continue
+        idx, d2 = eng.get_nn(e)
+        assert idx.min() >= 0 and idx.max() < N
+        # (a) the reported distance is the distance to the reported point, in the reference's arithmetic
+        ks = rng.choice(N, 2000, replace=False)
+        q = oracle.edge_queries(sc["pts"][s][ks], sc["poses_init"][s], sc["poses_init"][d])
+        p = sc["pts"][d][idx[ks]]
+        dd = q - p
+        assert np.array_equal(((dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]) + dd[:, 2] * dd[:, 2]).view(np.uint64), d2[ks].view(np.uint64))
+        # (b) exactness on the sample against the oracle tree
+        ri, rd = oracle.KdIndex(sc["pts"][d], "kd").closest_points(sc["pts"][s][ks], sc["poses_init"][s], sc["poses_init"][d], threads=8)
+        assert np.array_equal(ri, idx[ks]) and np.array_equal(rd.view(np.uint64), d2[ks].view(np.uint64))
+        # (c) list is sorted by src index, weight = float(1.5 * upper median of the inlier distances)
+        f, sec, dist, w = eng.get_edge(e)
+        assert np.all(np.diff(f) > 0)
+        med = np.sort(dist)[len(dist) // 2]
+        assert np.float32(w) == np.float32(med * 1.5)
+    eng.close()
