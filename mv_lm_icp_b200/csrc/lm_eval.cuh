@@ -11,9 +11,13 @@
 // x = T_k^-1 T_s p = R_rel p + t_rel, d = x - q; p2p: r = d, p2plane: r = d . n.  With the canonical body tangent
 // xi = (upsilon, omega) of T_s <- T_s exp(xi):   dr/dxi_s = [m ; p x m],  m = R_rel^T n   (p2plane)
 //                                                 J_s = R_rel [I | -[p]x]               (p2p)
-// and the dst-side Jacobian is J_k = -J_s Ad(T_rel^-1) for every residual, so ONE 6x6 block A = sum w J_s^T J_s,
-// one 6-vector b = sum w J_s^T r and the cost are accumulated per edge (28 doubles); lm_step.cuh expands them to
-// the (s,s),(s,k),(k,k) blocks and maps the canonical tangent to the active parameterisation (tangent_map()).
+// point-to-plane (scalar residual): the dst-side row is J_k = -J_s Ad(T_rel^-1), so ONE 6x6 block A = sum w J_s^T J_s,
+// one 6-vector b = sum w J_s^T r and the cost are accumulated per edge; lm_step.cuh expands them to the (s,s),(s,k),
+// (k,k) blocks and maps the canonical tangent to the active parameterisation (tangent_map()).
+// point-to-point (3-vector residual expressed in WORLD axes by the reference): the cost and the gradient are the
+// same in any frame, but the Gauss-Newton matrix is not (the residual axes rotate with T_k), so the world-frame rows
+// J_s = R_s [I | -[p]x], J_k = -R_k [I | -[q]x] are used: J^T J is then a function of the moments sum w, sum w p,
+// sum w q, sum w pp^T, sum w qq^T, sum w pq^T (28 doubles) which is what the kernel accumulates.
 // Bytes per correspondence: idx 4 + src 16 + dst 16 (+ normal 16) = 36 / 52 B in the fp32-storage mode.
 #pragma once
 #include <cuda_runtime.h>
@@ -31,7 +35,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// partial[tile][NBLK]: A upper triangle row-major (21), b (6), cost (1)
+// partial[tile][NBLK]: layout BLK_* of types.cuh
 template <bool F32, int COST>
 __global__ void __launch_bounds__(EVAL_THREADS)
 lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
@@ -64,7 +68,8 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
   for (int i = 0; i < 21; ++i) A[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) g[i] = 0.0;
-  double sw = 0.0, swp[3] = {0, 0, 0}, swpp[6] = {0, 0, 0, 0, 0, 0};   // p2p structure: sum w, sum w p, sum w p p^T
+  double sw = 0.0, swp[3] = {0, 0, 0}, swq[3] = {0, 0, 0}, swpp[6] = {0, 0, 0, 0, 0, 0}, swqq[6] = {0, 0, 0, 0, 0, 0},
+         swpq[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // point-to-point moments
 
   const int end = min(t.start + tile_len, e.n_src);
   for (int k = t.start + threadIdx.x; k < end; k += EVAL_THREADS) {
@@ -114,33 +119,42 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
       g[3] += w * (py * u2 - pz * u1); g[4] += w * (pz * u0 - px * u2); g[5] += w * (px * u1 - py * u0);
       sw += w;
       const double wx = w * px, wy = w * py, wz = w * pz;
+      const double vx = w * qx, vy = w * qy, vz = w * qz;
       swp[0] += wx; swp[1] += wy; swp[2] += wz;
+      swq[0] += vx; swq[1] += vy; swq[2] += vz;
       swpp[0] += wx * px; swpp[1] += wx * py; swpp[2] += wx * pz; swpp[3] += wy * py; swpp[4] += wy * pz; swpp[5] += wz * pz;
+      swqq[0] += vx * qx; swqq[1] += vx * qy; swqq[2] += vx * qz; swqq[3] += vy * qy; swqq[4] += vy * qz; swqq[5] += vz * qz;
+      swpq[0] += wx * qx; swpq[1] += wx * qy; swpq[2] += wx * qz;
+      swpq[3] += wy * qx; swpq[4] += wy * qy; swpq[5] += wy * qz;
+      swpq[6] += wz * qx; swpq[7] += wz * qy; swpq[8] += wz * qz;
     }
   }
-  if (COST == COST_P2P || COST == COST_MIXED) {
-    // sum w J^T J with J = R_rel [I | -[p]x]:  [[w I, -w[p]x], [w[p]x, w(|p|^2 I - p p^T)]]
-    // U(i,j): index of (i,j), i <= j, in the row-major upper triangle
-    auto U = [](int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); };
-    A[U(0, 0)] += sw; A[U(1, 1)] += sw; A[U(2, 2)] += sw;
-    A[U(0, 4)] += swp[2];  A[U(0, 5)] += -swp[1];
-    A[U(1, 3)] += -swp[2]; A[U(1, 5)] += swp[0];
-    A[U(2, 3)] += swp[1];  A[U(2, 4)] += -swp[0];
-    const double trp = swpp[0] + swpp[3] + swpp[5];
-    A[U(3, 3)] += trp - swpp[0]; A[U(3, 4)] += -swpp[1]; A[U(3, 5)] += -swpp[2];
-    A[U(4, 4)] += trp - swpp[3]; A[U(4, 5)] += -swpp[4];
-    A[U(5, 5)] += trp - swpp[5];
-  }
-
   // block reduction: warp shuffles, then one value per warp through shared memory, fixed order
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int NUSED = (COST == COST_P2PLANE) ? NBLK_PLANE : NBLK;
+#define MV_RED(val, slot) { const double v_ = warp_sum(val); if (lane == 0) sred[wid][slot] = v_; }
+  if (COST != COST_P2P) {
 #pragma unroll
-  for (int i = 0; i < 21; ++i) { const double v = warp_sum(A[i]); if (lane == 0) sred[wid][i] = v; }
+    for (int i = 0; i < 21; ++i) MV_RED(A[i], BLK_A + i)
+  } else if (lane == 0) {
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { const double v = warp_sum(g[i]); if (lane == 0) sred[wid][21 + i] = v; }
-  { const double v = warp_sum(cost); if (lane == 0) sred[wid][27] = v; }
+    for (int i = 0; i < 21; ++i) sred[wid][BLK_A + i] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) MV_RED(g[i], BLK_B + i)
+  MV_RED(cost, BLK_COST)
+  if (COST != COST_P2PLANE) {
+    MV_RED(sw, BLK_SW)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { MV_RED(swp[i], BLK_SWP + i) MV_RED(swq[i], BLK_SWQ + i) }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { MV_RED(swpp[i], BLK_SWPP + i) MV_RED(swqq[i], BLK_SWQQ + i) }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) MV_RED(swpq[i], BLK_SWPQ + i)
+  }
+#undef MV_RED
   __syncthreads();
-  if (threadIdx.x < NBLK) {
+  if (threadIdx.x < NUSED) {
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < EVAL_THREADS / 32; ++w) v += sred[w][threadIdx.x];
@@ -150,9 +164,10 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
 
 // blocks[e][NBLK] = sum of the edge's tile partials in tile order (deterministic); zero for edges not owned.
 __global__ void lm_reduce_kernel(const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
-                                 double* __restrict__ blocks) {
+                                 double* __restrict__ blocks, int nused) {
   const int e = blockIdx.x, j = threadIdx.x;
   if (j >= NBLK) return;
+  if (j >= nused) { blocks[(size_t)e * NBLK + j] = 0.0; return; }
   double v = 0.0;
   for (int t = edge_tile_begin[e]; t < edge_tile_begin[e + 1]; ++t) v += partial[(size_t)t * NBLK + j];
   blocks[(size_t)e * NBLK + j] = v;

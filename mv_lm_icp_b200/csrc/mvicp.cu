@@ -83,13 +83,15 @@ struct mvicp_ctx {
   std::vector<float> h_weight; std::vector<unsigned long long> h_count;
   // LM
   DevBuf d_state, d_x, d_cand, d_Rt, d_K, d_col, d_H, d_g, d_Hc, d_gc, d_scale, d_diag, d_L, d_rhs, d_step,
-      d_Bs, d_ABs, d_Hp, d_gp, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather;
+      d_Qs, d_AQ, d_Hcan, d_T1, d_Hp, d_gp, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather;
   int n_free = 0, n_hblocks = 0;
   std::vector<int32_t> h_col;
   int32_t* h_done = nullptr;   // pinned
   // stats
   mvicp_stats stats{};
   cudaEvent_t ev[8]{};
+  std::vector<cudaEvent_t> eval_ev;   // pairs around every lm_eval launch of the last optimize
+  int eval_ev_used = 0;
   bool ev_knn = false, ev_lm = false;
   float lm_eval_acc = 0.f;
 };
@@ -219,11 +221,12 @@ void mvicp_destroy(mvicp_ctx* c) {
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
                     &c->d_weight, &c->d_median, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
                     &c->d_blocks, &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
-                    &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_Bs, &c->d_ABs, &c->d_Hp, &c->d_gp,
+                    &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_Qs, &c->d_AQ, &c->d_Hcan, &c->d_T1, &c->d_Hp, &c->d_gp,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
                     &c->d_gc_side, &c->d_posegather};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
   if (c->h_done) cudaFreeHost(c->h_done);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -533,7 +536,8 @@ static int prepare_lm(mvicp_ctx* c, int n) {
   RET(c->d_H.reserve(sizeof(double) * n * n)); RET(c->d_Hc.reserve(sizeof(double) * n * n)); RET(c->d_L.reserve(sizeof(double) * n * n));
   RET(c->d_g.reserve(sizeof(double) * n)); RET(c->d_gc.reserve(sizeof(double) * n)); RET(c->d_scale.reserve(sizeof(double) * n));
   RET(c->d_diag.reserve(sizeof(double) * n)); RET(c->d_rhs.reserve(sizeof(double) * n)); RET(c->d_step.reserve(sizeof(double) * n));
-  RET(c->d_Bs.reserve(sizeof(double) * 72 * E)); RET(c->d_ABs.reserve(sizeof(double) * 72 * E));
+  RET(c->d_Qs.reserve(sizeof(double) * 36 * E)); RET(c->d_AQ.reserve(sizeof(double) * 36 * E));
+  RET(c->d_Hcan.reserve(sizeof(double) * 144 * E)); RET(c->d_T1.reserve(sizeof(double) * 144 * E));
   RET(c->d_Hp.reserve(sizeof(double) * 144 * E)); RET(c->d_gp.reserve(sizeof(double) * 12 * E));
   return MVICP_OK;
 }
@@ -622,7 +626,8 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   w.gb_ptr = c->d_gb_ptr.as<int32_t>(); w.gc_edge = c->d_gc_edge.as<int32_t>(); w.gc_side = c->d_gc_side.as<int32_t>();
   w.H = c->d_H.as<double>(); w.g = c->d_g.as<double>(); w.Hc = c->d_Hc.as<double>(); w.gc = c->d_gc.as<double>();
   w.scale = c->d_scale.as<double>(); w.diag = c->d_diag.as<double>(); w.Lg = c->d_L.as<double>(); w.rhs = c->d_rhs.as<double>();
-  w.step = c->d_step.as<double>(); w.Bs = c->d_Bs.as<double>(); w.ABs = c->d_ABs.as<double>(); w.Hp = c->d_Hp.as<double>();
+  w.step = c->d_step.as<double>(); w.Qs = c->d_Qs.as<double>(); w.AQ = c->d_AQ.as<double>(); w.Hcan = c->d_Hcan.as<double>();
+  w.T1 = c->d_T1.as<double>(); w.Hp = c->d_Hp.as<double>();
   w.gp = c->d_gp.as<double>(); w.poses16 = c->d_poses.as<double>();
   const size_t l_bytes = sizeof(double) * (size_t)n * n;
   w.l_in_smem = l_bytes <= 200 * 1024 ? 1 : 0;
@@ -634,9 +639,15 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   c->stats.kernel_launches += 1;
   int evals = 0;
   const int max_evals = opt.max_num_iterations + 2;
+  c->eval_ev_used = 0;
   while (true) {
+    if ((int)c->eval_ev.size() < c->eval_ev_used + 2) { cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); c->eval_ev.push_back(a); c->eval_ev.push_back(b); }
+    CU(cudaEventRecord(c->eval_ev[c->eval_ev_used], c->stream));
     if (c->f32) launch_eval<true>(c, cost, st.robust); else launch_eval<false>(c, cost, st.robust);
-    lm_reduce_kernel<<<E, 32, 0, c->stream>>>(c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(), c->d_blocks.as<double>());
+    CU(cudaEventRecord(c->eval_ev[c->eval_ev_used + 1], c->stream));
+    c->eval_ev_used += 2;
+    lm_reduce_kernel<<<E, 64, 0, c->stream>>>(c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(), c->d_blocks.as<double>(),
+                                             cost == COST_P2PLANE ? NBLK_PLANE : NBLK);
     if (c->comm && c->world > 1)
       NC(ncclAllReduce(c->d_blocks.p, c->d_blocks.p, (size_t)NBLK * E, ncclDouble, ncclSum, c->comm, c->stream));
     lm_step_kernel<<<1, STEP_THREADS, dyn, c->stream>>>(w);
@@ -741,7 +752,12 @@ int mvicp_get_stats(mvicp_ctx* c, mvicp_stats* out) {
     cudaEventElapsedTime(&c->stats.select_ms, c->ev[1], c->ev[2]);
     c->stats.correspond_ms = c->stats.knn_ms + c->stats.select_ms;
   }
-  if (c->ev_lm) cudaEventElapsedTime(&c->stats.optimize_ms, c->ev[3], c->ev[4]);
+  if (c->ev_lm) {
+    cudaEventElapsedTime(&c->stats.optimize_ms, c->ev[3], c->ev[4]);
+    float acc = 0.f;
+    for (int i = 0; i + 1 < c->eval_ev_used; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, c->eval_ev[i], c->eval_ev[i + 1]); acc += ms; }
+    c->stats.lm_eval_ms = acc; c->stats.lm_other_ms = c->stats.optimize_ms - acc;
+  }
   if (c->E && fetch_edge_meta(c) == MVICP_OK) {
     int64_t s = 0; for (int e = 0; e < c->E; ++e) if (c->h_edges[e].owned) s += (int64_t)c->h_count[e];
     c->stats.correspondences = s;

@@ -17,7 +17,12 @@ constexpr int LEAF = 8;          // points per BVH leaf
 constexpr int KNN_TILE = 256;    // queries per CTA of the NN kernel
 constexpr int EVAL_TILE = 2048;  // correspondence slots per CTA of the LM streaming kernel
 constexpr int EVAL_THREADS = 256;
-constexpr int NBLK = 28;         // per-edge block: 21 (upper 6x6) + 6 (rhs) + 1 (cost)
+// per-edge block (doubles):  A = upper 6x6 of the point-to-plane normal matrix in the src frame's canonical tangent,
+// b = rhs (both costs), cost, then the point-to-point moments sum w, sum w p, sum w q, sum w pp^T, sum w qq^T, sum w pq^T
+constexpr int BLK_A = 0, BLK_B = 21, BLK_COST = 27, BLK_SW = 28, BLK_SWP = 29, BLK_SWQ = 32, BLK_SWPP = 35, BLK_SWQQ = 41,
+              BLK_SWPQ = 47;
+constexpr int NBLK_PLANE = 28;   // entries used by a point-to-plane-only solve
+constexpr int NBLK = 56;         // stride of a block
 
 struct Box { float lo[3]; float hi[3]; float pad[2]; };   // 32 B; child pairs are 64-B contiguous
 

@@ -22,18 +22,36 @@ def _rot(axis, a):
 
 # (centre, radii, rotation)
 _PARTS = [
-    ((0.000, 0.000, 0.000), (0.055, 0.045, 0.040), np.eye(3)),                       # body
-    ((0.050, 0.000, 0.045), (0.030, 0.027, 0.027), np.eye(3)),                       # head
-    ((0.045, -0.016, 0.095), (0.009, 0.006, 0.036), _rot(0, 0.25) @ _rot(1, -0.2)),  # ear
-    ((0.045, 0.016, 0.095), (0.009, 0.006, 0.036), _rot(0, -0.25) @ _rot(1, -0.2)),  # ear
-    ((-0.058, 0.000, 0.005), (0.012, 0.012, 0.012), np.eye(3)),                      # tail
-    ((-0.020, -0.034, -0.026), (0.036, 0.015, 0.018), _rot(2, 0.2)),                 # hind leg
-    ((-0.020, 0.034, -0.026), (0.036, 0.015, 0.018), _rot(2, -0.2)),                 # hind leg
-    ((0.040, -0.020, -0.034), (0.020, 0.010, 0.010), np.eye(3)),                     # front paw
-    ((0.040, 0.020, -0.034), (0.020, 0.010, 0.010), np.eye(3)),                      # front paw
-    ((0.075, 0.000, 0.040), (0.010, 0.012, 0.010), np.eye(3)),                       # nose
+    ((0.000, 0.000, 0.000), (0.075, 0.040, 0.048), _rot(1, 0.25)),                   # body (elongated, pitched)
+    ((0.070, 0.004, 0.050), (0.030, 0.024, 0.027), _rot(2, 0.3)),                    # head
+    ((0.060, -0.016, 0.105), (0.010, 0.006, 0.042), _rot(0, 0.30) @ _rot(1, -0.35)), # ear
+    ((0.064, 0.020, 0.100), (0.010, 0.006, 0.038), _rot(0, -0.45) @ _rot(1, -0.10)), # ear
+    ((-0.078, 0.000, 0.020), (0.014, 0.014, 0.014), np.eye(3)),                      # tail
+    ((-0.030, -0.036, -0.030), (0.040, 0.016, 0.022), _rot(2, 0.25)),                # hind leg
+    ((-0.030, 0.036, -0.030), (0.040, 0.016, 0.022), _rot(2, -0.25)),                # hind leg
+    ((0.050, -0.022, -0.040), (0.024, 0.010, 0.011), _rot(2, -0.1)),                 # front paw
+    ((0.052, 0.020, -0.040), (0.022, 0.010, 0.011), _rot(2, 0.15)),                  # front paw
+    ((0.098, 0.006, 0.046), (0.010, 0.012, 0.010), np.eye(3)),                       # nose
 ]
-_CENTRE = np.array([0.0, 0.0, 0.03])
+_CENTRE = np.array([0.01, 0.0, 0.03])
+
+
+def _add_bumps():
+    """Deterministic surface detail (small spheres half-sunk into body and head) so that the shape has no sliding
+    directions: a union of a few smooth ellipsoids alone lets point-to-plane ICP rotate freely about their axes."""
+    rng = np.random.default_rng(0xB077)
+    for (c, r, R) in list(_PARTS[:2]):
+        k = 0
+        while k < 14:
+            u = rng.normal(size=3); u /= np.linalg.norm(u)
+            pos = np.asarray(c) + R @ (np.asarray(r) * u)
+            rad = rng.uniform(0.006, 0.013)
+            _PARTS.append((tuple(pos), (rad, rad * rng.uniform(0.6, 1.0), rad * rng.uniform(0.6, 1.0)),
+                           _rot(0, rng.uniform(0, 3)) @ _rot(2, rng.uniform(0, 3))))
+            k += 1
+
+
+_add_bumps()
 
 
 def _cast(o, d):
@@ -87,7 +105,7 @@ def _so3_exp(w):
     return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
 
 
-def make_view(v, n_views, n_points, seed, depth_sigma=5e-5, half_fov=0.27):
+def make_view(v, n_views, n_points, seed, depth_sigma=5e-5, half_fov=0.30):
     rng = np.random.default_rng(seed)
     P = _camera_pose(2.0 * np.pi * v / n_views)
     R, pos = P[:3, :3], P[:3, 3]
