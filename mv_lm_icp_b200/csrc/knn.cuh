@@ -9,10 +9,8 @@
 //     point its traversal meets (nanoflann.hpp:1210) -- documented deviation, counted by the tests;
 //   * cutoff           sqrt(d2) < (double)thresh                 frame.cpp:142,156.
 //
-// Search structure: implicit binary AABB tree over Morton-sorted leaves (types.cuh).  Pruning is exact:
-// a box's lower bound is evaluated with the SAME rounded operation sequence as the point distance and every
-// operation is monotone, so lb(box) <= d2(point) for every point inside; a subtree is skipped only when
-// lb > best (strict), which also keeps all equal-distance candidates reachable for the tie rule.
+// Search structure: implicit binary AABB tree over leaves in left-balanced KD order (types.cuh), walked in fp32 with a
+// conservative screen and re-ranked in fp64 (see "fp32 screening" below): the answer is the exact fp64 arg-min.
 #pragma once
 #include <cuda_runtime.h>
 #include <limits.h>
@@ -51,46 +49,126 @@ __device__ __forceinline__ double box_lb(const Box* __restrict__ boxes, int node
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-// Exact 1-NN of (qx,qy,qz) in frame fd.  best/bi may carry a seed (a valid candidate and its distance).
+// ---- fp32 screening + fp64 exact re-rank ------------------------------------------------------------------------
+// The tree is walked in fp32.  A candidate (or a box) is looked at exactly only if its fp32 distance does not exceed
+// bound32, an upper bound -- rounded up, with the fp32 error budget added -- of the current exact best:
+//   per-axis error of an fp32 difference (query rounded to fp32, rounded subtraction; stored coordinates exact in the
+//   fp32 storage mode, rounded in the fp64 mode)  <= delta = 2^-23 (|q|_inf + absmax)
+//   => computed d32 <= (D + sqrt(3) delta)^2 (1 + 2^-24)^3 for a point at true distance D (same for a box lower bound),
+//   so every point with D^2 <= best satisfies d32 <= bound32 := ru[(sqrt(best) + ea)^2 (1 + 1e-6)], ea = 2 sqrt(3) delta.
+// Whatever passes the screen is re-evaluated with the reference's fp64 operation sequence (d2_rn) on the exact
+// coordinates, and only that value decides: the result is the exact arg-min with the lowest-index tie rule.
+struct NNQuery {
+  double qx, qy, qz;     // exact query (dst-local)
+  float fx, fy, fz;      // fp32 rounding of it
+  double ea;             // absolute error allowance on a distance
+  double best; int bi;   // exact best so far
+  float bound32;
+};
+
+__device__ __forceinline__ void nn_tighten(NNQuery& s) {
+  const double r = sqrt(s.best) + s.ea;
+  s.bound32 = __double2float_ru(r * r * (1.0 + 1e-6));
+}
+
+__device__ __forceinline__ float box_lb32(const Box* __restrict__ boxes, int node, const NNQuery& s) {
+  const float4* b = reinterpret_cast<const float4*>(boxes + node);
+  const float4 u = __ldg(b), v = __ldg(b + 1);   // u = lo.xyz, hi.x ; v = hi.yz
+  const float dx = fmaxf(fmaxf(u.x - s.fx, s.fx - u.w), 0.f);
+  const float dy = fmaxf(fmaxf(u.y - s.fy, s.fy - v.x), 0.f);
+  const float dz = fmaxf(fmaxf(u.z - s.fz, s.fz - v.y), 0.f);
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
 template <bool F32>
-__device__ __forceinline__ void nn_search(const FrameDev& fd, double qx, double qy, double qz, double& best, int& bi) {
+__device__ __forceinline__ void nn_scan_leaf(const FrameDev& fd, int leaf, NNQuery& s) {
+  const int64_t b = (int64_t)leaf * LEAF;
+  const int cnt = min(LEAF, fd.n - (int)b);
+#pragma unroll 4
+  for (int i = 0; i < cnt; ++i) {
+    const float4 r = __ldg(fd.pts_sf + b + i);
+    const float dx = s.fx - r.x, dy = s.fy - r.y, dz = s.fz - r.z;
+    const float d32 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (d32 <= s.bound32) {
+      double px, py, pz; int pi;
+      if (F32) { px = (double)r.x; py = (double)r.y; pz = (double)r.z; pi = __float_as_int(r.w); }
+      else Rec<false>::load(fd.pts_s, b + i, px, py, pz, pi);
+      const double d = d2_rn(s.qx, s.qy, s.qz, px, py, pz);
+      if (d < s.best || (d == s.best && pi < s.bi)) { s.best = d; s.bi = pi; nn_tighten(s); }
+    }
+  }
+}
+
+// depth-first search of the subtree rooted at `root` (near child first), pruning with bound32
+template <bool F32>
+__device__ __forceinline__ void nn_dfs(const FrameDev& fd, int root, NNQuery& s) {
   const int L = fd.n_leaf_pad;
-  int stk_n[20]; double stk_lb[20]; int sp = 0;
-  int node = 1;
-  if (box_lb(fd.boxes, 1, qx, qy, qz) > best) return;
+  int stk_n[20]; float stk_lb[20]; int sp = 0;
+  int node = root;
   while (true) {
     if (node >= L) {
-      const int64_t b = (int64_t)(node - L) * LEAF;
-      const int cnt = min(LEAF, fd.n - (int)b);
-#pragma unroll 1
-      for (int i = 0; i < cnt; ++i) {
-        double px, py, pz; int pi;
-        Rec<F32>::load(fd.pts_s, b + i, px, py, pz, pi);
-        const double d = d2_rn(qx, qy, qz, px, py, pz);
-        if (d < best || (d == best && pi < bi)) { best = d; bi = pi; }
-      }
+      nn_scan_leaf<F32>(fd, node - L, s);
     } else {
       const int c0 = 2 * node;
-      const double l0 = box_lb(fd.boxes, c0, qx, qy, qz), l1 = box_lb(fd.boxes, c0 + 1, qx, qy, qz);
+      const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
       const bool first0 = l0 <= l1;
-      const double ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
-      if (ln <= best) {
-        if (lf <= best) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+      const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
+      if (ln <= s.bound32) {
+        if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
         node = first0 ? c0 : c0 + 1;
         continue;
       }
     }
-    // pop
     bool found = false;
     while (sp > 0) {
       --sp;
-      if (stk_lb[sp] <= best) { node = stk_n[sp]; found = true; break; }
+      if (stk_lb[sp] <= s.bound32) { node = stk_n[sp]; found = true; break; }
     }
     if (!found) break;
   }
 }
 
-// One thread per (edge, src point) query; src points are walked in the src frame's Morton order so that the
+// Exact 1-NN.  start_leaf >= 0: the leaf holding a good guess (previous round's match); < 0: greedy descent.
+// Equivalent to a full depth-first search whose first root-to-leaf path is given: the start leaf is scanned, then the
+// sibling subtree of every ancestor, bottom-up (nearest first), is searched if its box can still hold a closer point.
+template <bool F32>
+__device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int start_leaf) {
+  const int L = fd.n_leaf_pad;
+  int leaf_node;
+  if (start_leaf < 0) {
+    int node = 1;
+    while (node < L) {
+      const int c0 = 2 * node;
+      const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
+      node = (l1 < l0) ? c0 + 1 : c0;
+    }
+    leaf_node = node;
+  } else leaf_node = L + start_leaf;
+  nn_scan_leaf<F32>(fd, leaf_node - L, s);
+  // phase 1 (lock-step across the warp, independent loads): which sibling subtrees can matter at all
+  unsigned mask = 0u;
+#pragma unroll 4
+  for (int l = 0; l < fd.depth; ++l)
+    mask |= (box_lb32(fd.boxes, (leaf_node >> l) ^ 1, s) <= s.bound32 ? 1u : 0u) << l;
+  // phase 2: search them bottom-up; the bound only shrinks, so each is re-checked when its turn comes
+  while (mask) {
+    const int l = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int sib = (leaf_node >> l) ^ 1;
+    if (box_lb32(fd.boxes, sib, s) <= s.bound32) nn_dfs<F32>(fd, sib, s);
+  }
+}
+
+__device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, double qz, float absmax) {
+  s.qx = qx; s.qy = qy; s.qz = qz;
+  s.fx = (float)qx; s.fy = (float)qy; s.fz = (float)qz;
+  const double m = fmax(fmax(fabs(qx), fabs(qy)), fabs(qz)) + (double)absmax;
+  s.ea = 2.0 * 1.7320508075688774 * 1.1920928955078125e-7 * m;
+  s.best = __longlong_as_double(0x7ff0000000000000LL); s.bi = INT_MAX;
+  s.bound32 = __int_as_float(0x7f800000);
+}
+
+// One thread per (edge, src point) query; src points are walked in the src frame's tree order so that the
 // lanes of a warp descend the dst tree together.
 template <bool F32>
 __global__ void __launch_bounds__(KNN_TILE)
@@ -124,18 +202,15 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
     const double qy = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[3], ex), __dmul_rn(sx.Rinv[4], ey)), __dmul_rn(sx.Rinv[5], ez));
     const double qz = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[6], ex), __dmul_rn(sx.Rinv[7], ey)), __dmul_rn(sx.Rinv[8], ez));
 
-    double best = __longlong_as_double(0x7ff0000000000000LL);
-    int bi = INT_MAX;
-    if (seed) {   // previous round's match: a valid upper bound, the search stays exact
-      const int s = seed[e.off + orig];
-      const int si = s >= 0 ? s : ~s;
-      if (si >= 0 && si < fd.n) {
-        double sxp, syp, szp; int dummy;
-        Rec<F32>::load(fd.pts_o, si, sxp, syp, szp, dummy);
-        best = d2_rn(qx, qy, qz, sxp, syp, szp); bi = si;
-      }
+    NNQuery nq; nn_query_init(nq, qx, qy, qz, fd.absmax);
+    int start_leaf = -1;
+    if (seed) {   // previous round's match: a valid first guess, the search stays exact
+      const int sd = seed[e.off + orig];
+      const int si = sd >= 0 ? sd : ~sd;
+      if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
     }
-    nn_search<F32>(fd, qx, qy, qz, best, bi);
+    nn_search<F32>(fd, nq, start_leaf);
+    const double best = nq.best; const int bi = nq.bi;
     const bool inlier = __dsqrt_rn(best) < thresh;
     corr[e.off + orig] = inlier ? bi : ~bi;
     d2out[e.off + orig] = best;
@@ -152,10 +227,9 @@ template <bool F32>
 __global__ void knn_single_kernel(const FrameDev* __restrict__ frames, int frame, double qx, double qy, double qz,
                                   long long* out_idx, double* out_d2) {
   const FrameDev fd = frames[frame];
-  double best = __longlong_as_double(0x7ff0000000000000LL);
-  int bi = INT_MAX;
-  nn_search<F32>(fd, qx, qy, qz, best, bi);
-  *out_idx = bi; *out_d2 = best;
+  NNQuery nq; nn_query_init(nq, qx, qy, qz, fd.absmax);
+  nn_search<F32>(fd, nq, -1);
+  *out_idx = nq.bi; *out_d2 = nq.best;
 }
 
 // Per-edge constants from the current poses (poses16: column-major 4x4 per frame), with the reference's

@@ -101,45 +101,53 @@ static inline int owner_of(const mvicp_ctx* c, int frame) { return (int)(((int64
 // =================================================================================================
 // one-time per-frame search structure (replaces the lazily built nanoflann index, frame.cpp:188-193)
 // =================================================================================================
-static inline uint64_t spread21(uint64_t v) {   // 21 bits -> every third bit
-  v &= 0x1fffffull;
-  v = (v | v << 32) & 0x1f00000000ffffull;
-  v = (v | v << 16) & 0x1f0000ff0000ffull;
-  v = (v | v << 8) & 0x100f00f00f00f00full;
-  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
-  v = (v | v << 2) & 0x1249249249249249ull;
-  return v;
-}
 static inline float f_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
 static inline float f_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
 
 struct HostFrameBuild {
-  std::vector<int32_t> order;      // Morton order -> original index
+  std::vector<int32_t> order;      // tree order -> original index
+  std::vector<int32_t> pos_of;     // original index -> tree position
   std::vector<Box> boxes;
-  int n_leaf_pad = 1;
+  int n_leaf_pad = 1, depth = 0;
+  float absmax = 0.f;
 };
+
+// Left-balanced KD ordering: the node that covers leaf slots [a, b) of the implicit tree holds the points at sorted
+// positions [LEAF a, min(LEAF b, n)); each internal node splits its points at the capacity of its left half along
+// the widest axis of their bounding box (nth_element), so sibling boxes never overlap and leaves are compact.
+static void kd_order(const double* pts, int32_t* idx, int64_t begin, int64_t count, int64_t leaf_slots) {
+  if (leaf_slots <= 1 || count <= LEAF) return;
+  const int64_t cap_left = (leaf_slots / 2) * LEAF;
+  if (count > cap_left) {
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = begin; i < begin + count; ++i)
+      for (int a = 0; a < 3; ++a) { const double v = pts[3 * (int64_t)idx[i] + a]; lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+    int ax = 0; for (int a = 1; a < 3; ++a) if (hi[a] - lo[a] > hi[ax] - lo[ax]) ax = a;
+    std::nth_element(idx + begin, idx + begin + cap_left, idx + begin + count, [&](int32_t x, int32_t y) {
+      const double vx = pts[3 * (int64_t)x + ax], vy = pts[3 * (int64_t)y + ax];
+      return vx < vy || (vx == vy && x < y);
+    });
+    kd_order(pts, idx, begin, cap_left, leaf_slots / 2);
+    kd_order(pts, idx, begin + cap_left, count - cap_left, leaf_slots / 2);
+  } else {
+    kd_order(pts, idx, begin, count, leaf_slots / 2);
+  }
+}
 
 static void build_frame(const double* pts, int64_t n, HostFrameBuild& out) {
   double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int64_t i = 0; i < n; ++i)
     for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], pts[3 * i + a]); hi[a] = std::max(hi[a], pts[3 * i + a]); }
-  double ext = 0; for (int a = 0; a < 3; ++a) ext = std::max(ext, hi[a] - lo[a]);
-  const double sc = ext > 0 ? 2097151.0 / ext : 0.0;
-  std::vector<std::pair<uint64_t, int32_t>> keyed(n);
-  for (int64_t i = 0; i < n; ++i) {
-    uint64_t c[3];
-    for (int a = 0; a < 3; ++a) {
-      double v = (pts[3 * i + a] - lo[a]) * sc;
-      c[a] = (uint64_t)std::min(2097151.0, std::max(0.0, v));
-    }
-    keyed[i] = {spread21(c[0]) | spread21(c[1]) << 1 | spread21(c[2]) << 2, (int32_t)i};
-  }
-  std::sort(keyed.begin(), keyed.end());
-  out.order.resize(n);
-  for (int64_t i = 0; i < n; ++i) out.order[i] = keyed[i].second;
   const int64_t n_leaf = std::max<int64_t>(1, (n + LEAF - 1) / LEAF);
   int L = 1; while (L < n_leaf) L <<= 1;
+  out.order.resize(n); out.pos_of.resize(n);
+  std::iota(out.order.begin(), out.order.end(), 0);
+  kd_order(pts, out.order.data(), 0, n, L);
+  for (int64_t i = 0; i < n; ++i) out.pos_of[out.order[i]] = (int32_t)i;
+  double am = 0; for (int a = 0; a < 3; ++a) am = std::max(am, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
+  out.absmax = f_up(am);
   out.n_leaf_pad = L;
+  out.depth = 0; while ((1 << out.depth) < L) ++out.depth;
   out.boxes.assign((size_t)2 * L, Box{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}, {0, 0}});
   for (int64_t l = 0; l < n_leaf; ++l) {
     Box& b = out.boxes[L + l];
@@ -263,7 +271,7 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
   std::vector<char> stage;
   for (int f = 0; f < M; ++f) {
     const int64_t n = n_pts[f];
-    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr;
+    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr;
     CU(cudaMalloc(&d_o, rec * n)); c->frame_allocs.push_back(d_o);
     CU(cudaMalloc(&d_s, rec * n)); c->frame_allocs.push_back(d_s);
     CU(cudaMalloc(&d_b, sizeof(Box) * builds[f].boxes.size())); c->frame_allocs.push_back(d_b);
@@ -278,7 +286,17 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
       CU(cudaMemcpy(d_n, stage.data(), rec * n, cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(d_b, builds[f].boxes.data(), sizeof(Box) * builds[f].boxes.size(), cudaMemcpyHostToDevice));
-    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const Box*)d_b, (int32_t)n, builds[f].n_leaf_pad};
+    if (f32) d_sf = d_s;
+    else {   // rounded fp32 copy used only to screen candidates; exact arithmetic reads pts_s
+      CU(cudaMalloc(&d_sf, sizeof(float4) * n)); c->frame_allocs.push_back(d_sf);
+      stage.resize(sizeof(float4) * n);
+      pack_records(true, pts[f], builds[f].order.data(), builds[f].order.data(), n, stage.data());
+      CU(cudaMemcpy(d_sf, stage.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMalloc(&d_pos, sizeof(int32_t) * n)); c->frame_allocs.push_back(d_pos);
+    CU(cudaMemcpy(d_pos, builds[f].pos_of.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const float4*)d_sf, (const Box*)d_b, (const int32_t*)d_pos, (int32_t)n,
+                              builds[f].n_leaf_pad, builds[f].depth, builds[f].absmax};
   }
   RET(c->d_frames.reserve(sizeof(FrameDev) * M));
   CU(cudaMemcpy(c->d_frames.p, c->h_frames.data(), sizeof(FrameDev) * M, cudaMemcpyHostToDevice));

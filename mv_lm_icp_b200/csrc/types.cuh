@@ -3,8 +3,8 @@
 // HBM layout.  Every frame keeps, resident for the life of the context:
 //   pts_o / nor_o : points / normals in the caller's order, one 16-byte (float4) or 32-byte (double4)
 //                   record each -> the LM kernel's coalesced src stream and its dst gathers;
-//   pts_s         : the same points in Morton order, record.w = original index -> NN search leaves;
-//   boxes         : implicit binary AABB tree over leaves of LEAF consecutive Morton-sorted points,
+//   pts_s         : the same points in left-balanced KD order ("tree order"), record.w = original index;
+//   boxes         : implicit binary AABB tree over leaves of LEAF consecutive tree-order points,
 //                   heap order (root = 1, children 2i, 2i+1, leaves at [n_leaf_pad, 2 n_leaf_pad)).
 // float storage is used iff every coordinate of every frame is exactly fp32-representable
 // (checked at upload); arithmetic is fp64 either way, so results do not depend on the choice.
@@ -29,12 +29,16 @@ struct Box { float lo[3]; float hi[3]; float pad[2]; };   // 32 B; child pairs a
 struct double4a { double x, y, z, w; };   // 32-byte record for the fp64 storage mode
 
 struct FrameDev {
-  const void* pts_o;     // float4* or double4a*
+  const void* pts_o;     // float4* or double4a*: exact coordinates, caller's order
   const void* nor_o;     // may be null
-  const void* pts_s;     // Morton order, .w = original index (int bits / int64 bits)
-  const Box* boxes;      // 2 * n_leaf_pad entries (entry 0 unused)
+  const void* pts_s;     // exact coordinates in tree order, .w = original index (int bits / int64 bits)
+  const float4* pts_sf;  // fp32 screening copy in tree order, .w = original index; == pts_s in the fp32 storage mode
+  const Box* boxes;      // 2 * n_leaf_pad entries (entry 0 unused), fp32, rounded outward
+  const int32_t* pos_of; // original index -> position in tree order (seed -> leaf)
   int32_t n;             // points
   int32_t n_leaf_pad;    // power of two >= ceil(n / LEAF)
+  int32_t depth;         // log2(n_leaf_pad)
+  float absmax;          // max |coordinate| of the cloud (bounds the fp32 rounding of a difference)
 };
 
 struct EdgeDev {
