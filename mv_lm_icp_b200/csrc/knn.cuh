@@ -55,20 +55,23 @@ __device__ __forceinline__ double box_lb(const Box* __restrict__ boxes, int node
 //   per-axis error of an fp32 difference (query rounded to fp32, rounded subtraction; stored coordinates exact in the
 //   fp32 storage mode, rounded in the fp64 mode)  <= delta = 2^-23 (|q|_inf + absmax)
 //   => computed d32 <= (D + sqrt(3) delta)^2 (1 + 2^-24)^3 for a point at true distance D (same for a box lower bound),
-//   so every point with D^2 <= best satisfies d32 <= bound32 := ru[(sqrt(best) + ea)^2 (1 + 1e-6)], ea = 2 sqrt(3) delta.
+//   so every point with D^2 <= best satisfies d32 <= bound32 := ru[(sqrt(best) + ea)^2 (1 + 1e-6)], ea = 2 sqrt(3) delta
+//   (bound32 itself is evaluated in fp32 with every operation rounded up).
 // Whatever passes the screen is re-evaluated with the reference's fp64 operation sequence (d2_rn) on the exact
 // coordinates, and only that value decides: the result is the exact arg-min with the lowest-index tie rule.
 struct NNQuery {
   double qx, qy, qz;     // exact query (dst-local)
   float fx, fy, fz;      // fp32 rounding of it
-  double ea;             // absolute error allowance on a distance
+  float eaf;             // absolute error allowance on a distance (rounded up)
   double best; int bi;   // exact best so far
   float bound32;
 };
 
 __device__ __forceinline__ void nn_tighten(NNQuery& s) {
-  const double r = sqrt(s.best) + s.ea;
-  s.bound32 = __double2float_ru(r * r * (1.0 + 1e-6));
+  // (sqrt(best) + ea)^2 (1 + 1e-6), evaluated upward in fp32: b >= best, r >= sqrt(b)
+  const float b = __double2float_ru(s.best);
+  const float r = __fsqrt_ru(b);
+  s.bound32 = __fmul_ru(__fmaf_ru(s.eaf, __fmaf_ru(2.0f, r, s.eaf), b), 1.000001f);
 }
 
 __device__ __forceinline__ float box_lb32(const Box* __restrict__ boxes, int node, const NNQuery& s) {
@@ -163,7 +166,7 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
   s.qx = qx; s.qy = qy; s.qz = qz;
   s.fx = (float)qx; s.fy = (float)qy; s.fz = (float)qz;
   const double m = fmax(fmax(fabs(qx), fabs(qy)), fabs(qz)) + (double)absmax;
-  s.ea = 2.0 * 1.7320508075688774 * 1.1920928955078125e-7 * m;
+  s.eaf = __double2float_ru(2.0 * 1.7320508075688774 * 1.1920928955078125e-7 * m);
   s.best = __longlong_as_double(0x7ff0000000000000LL); s.bi = INT_MAX;
   s.bound32 = __int_as_float(0x7f800000);
 }
@@ -174,22 +177,19 @@ template <bool F32>
 __global__ void __launch_bounds__(KNN_TILE)
 knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
            const Tile* __restrict__ tiles, int32_t* __restrict__ corr, double* __restrict__ d2out,
-           const int32_t* __restrict__ seed, unsigned long long* __restrict__ edge_count, double thresh) {
+           const int32_t* __restrict__ seed, double thresh) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ EdgeXf sx;
-  __shared__ int s_cnt;
   {
     const double* g = reinterpret_cast<const double*>(xfs + t.edge);
     double* s = reinterpret_cast<double*>(&sx);
     for (int i = threadIdx.x; i < (int)(sizeof(EdgeXf) / sizeof(double)); i += blockDim.x) s[i] = g[i];
-    if (threadIdx.x == 0) s_cnt = 0;
   }
   __syncthreads();
   const FrameDev fs = frames[e.src];
   const FrameDev fd = frames[e.dst];
   const int ks = t.start + threadIdx.x;
-  int inl = 0;
   if (ks < e.n_src) {
     double px, py, pz; int orig;
     Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
@@ -214,13 +214,7 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
     const bool inlier = __dsqrt_rn(best) < thresh;
     corr[e.off + orig] = inlier ? bi : ~bi;
     d2out[e.off + orig] = best;
-    inl = inlier ? 1 : 0;
   }
-  // inlier count of the edge (integer atomics: order-independent)
-  const unsigned m = __ballot_sync(0xffffffffu, inl);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
-  __syncthreads();
-  if (threadIdx.x == 0 && s_cnt) atomicAdd(edge_count + t.edge, (unsigned long long)s_cnt);
 }
 
 template <bool F32>

@@ -83,36 +83,42 @@ __global__ void lm_init_kernel(LmWork w) {
   for (int i = 0; i < 36; ++i) w.K_eval[36 * f + i] = K[i];
 }
 
-// ---- dense Cholesky solve on L (n x n row-major, lower part used), rhs overwritten by the solution ----------
-__device__ bool chol_solve(double* L, double* y, int n) {
-  const int T = blockDim.x, tid = threadIdx.x;
+// ---- dense Cholesky solve --------------------------------------------------------------------------------------
+// L: (n+1) rows of stride ld; rows 0..n-1 hold the lower triangle of the SPD matrix, row n holds the right-hand side.
+// Right-looking factorisation; treating the rhs as an extra row performs the forward substitution for free.  Each
+// scaled column is stashed contiguously (colj) so the rank-1 update reads conflict-free; the diagonal of the factor
+// goes to dg.  The back substitution runs in one warp (shuffle-free, __syncwarp only).  Solution returned in y[0..n).
+__device__ bool chol_solve(double* L, int ld, int n, double* colj, double* dg, double* y) {
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   for (int j = 0; j < n; ++j) {
     __syncthreads();
-    const double d = L[(size_t)j * n + j];
+    const double d = L[(size_t)j * ld + j];
     if (!(d > 0.0) || !isfinite(d)) return false;     // uniform: every thread reads the same value
-    const double sd = sqrt(d);
+    const double sd = sqrt(d), inv = 1.0 / sd;
+    for (int r = j + tid; r <= n; r += T) {
+      if (r == j) { colj[j] = sd; dg[j] = sd; }
+      else { const double v = L[(size_t)r * ld + j] * inv; L[(size_t)r * ld + j] = v; colj[r] = v; }
+    }
     __syncthreads();
-    for (int i = j + tid; i < n; i += T) L[(size_t)i * n + j] = (i == j) ? sd : L[(size_t)i * n + j] / sd;
-    __syncthreads();
-    const int m = n - 1 - j;
-    for (int idx = tid; idx < m * m; idx += T) {
-      const int r = idx / m, c = idx - r * m;
-      if (c <= r) L[(size_t)(j + 1 + r) * n + j + 1 + c] -= L[(size_t)(j + 1 + r) * n + j] * L[(size_t)(j + 1 + c) * n + j];
+    for (int r = j + 1 + wid; r <= n; r += nw) {
+      const double lr = colj[r];
+      double* row = L + (size_t)r * ld;
+      const int cend = min(r, n - 1);
+      for (int c = j + 1 + lane; c <= cend; c += 32) row[c] -= lr * colj[c];
     }
   }
-  for (int j = 0; j < n; ++j) {          // L z = y
-    __syncthreads();
-    const double yj = y[j] / L[(size_t)j * n + j];
-    __syncthreads();
-    if (tid == 0) y[j] = yj;
-    for (int i = j + 1 + tid; i < n; i += T) y[i] -= L[(size_t)i * n + j] * yj;
-  }
-  for (int j = n - 1; j >= 0; --j) {     // L^T x = z
-    __syncthreads();
-    const double yj = y[j] / L[(size_t)j * n + j];
-    __syncthreads();
-    if (tid == 0) y[j] = yj;
-    for (int i = tid; i < j; i += T) y[i] -= L[(size_t)j * n + i] * yj;
+  __syncthreads();
+  for (int i = tid; i < n; i += T) y[i] = L[(size_t)n * ld + i];   // forward-substituted rhs
+  __syncthreads();
+  if (wid == 0) {
+    for (int j = n - 1; j >= 0; --j) {     // L^T x = z
+      const double yj = y[j] / dg[j];
+      __syncwarp();
+      if (lane == 0) y[j] = yj;
+      const double* row = L + (size_t)j * ld;
+      for (int i = lane; i < j; i += 32) y[i] -= row[i] * yj;
+      __syncwarp();
+    }
   }
   __syncthreads();
   return true;
@@ -126,7 +132,9 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   if (S->done) return;
   const int tid = threadIdx.x, T = blockDim.x;
   const int n = S->n, M = S->M, E = S->E, param = S->param;
-  double* L = w.l_in_smem ? smem : w.Lg;
+  // dynamic shared memory: [colj (n+1) | dg (n+1) | L (n+1) x (n|1) when it fits]
+  double* colj = smem; double* dg = smem + (S->n + 1);
+  double* L = w.l_in_smem ? smem + 2 * (S->n + 1) : w.Lg;
 
   // ================= 1. assemble Hc, gc, cost at the evaluation point ===============================
   // Canonical pair matrix per edge (12x12 over [xi_s, xi_k]):
@@ -357,15 +365,17 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
         w.diag[j] = fmin(fmax(d, S->opt.min_lm_diagonal), S->opt.max_lm_diagonal);
       }
     __syncthreads();
+    const int ldl = n | 1;   // odd stride: conflict-free column walks
     for (int idx = tid; idx < n * n; idx += T) {
       const int i = idx / n, j = idx - i * n;
+      if (j > i) continue;
       double v = w.scale[i] * w.H[idx] * w.scale[j];
-      if (i == j) { const double ld = sqrt(w.diag[i] / radius); v += ld * ld; }
-      L[idx] = v;
+      if (i == j) { const double ldg = sqrt(w.diag[i] / radius); v += ldg * ldg; }
+      L[(size_t)i * ldl + j] = v;
     }
-    for (int j = tid; j < n; j += T) w.rhs[j] = w.scale[j] * w.g[j];
+    for (int j = tid; j < n; j += T) L[(size_t)n * ldl + j] = w.scale[j] * w.g[j];
     __syncthreads();
-    bool ok = chol_solve(L, w.rhs, n);
+    bool ok = chol_solve(L, ldl, n, colj, dg, w.rhs);
     double bad = 0.0;
     if (ok) for (int j = tid; j < n; j += T) if (!isfinite(w.rhs[j])) bad = 1.0;
     bad = block_sum(bad, red);
@@ -374,11 +384,12 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     if (ok) {
       for (int j = tid; j < n; j += T) w.step[j] = -w.rhs[j];
       __syncthreads();
-      double acc = 0.0;   // -(s.g~) - 1/2 s^T H~ s
+      // model_cost_change = -(J s).(r + J s / 2) = -s.g~ - 1/2 s^T H~ s; with (H~ + D^2) y = g~ and s = -y this is
+      // 1/2 (y.g~ + sum D_i^2 y_i^2): O(n) instead of O(n^2)
+      double acc = 0.0;
       for (int i = tid; i < n; i += T) {
-        double row = 0.0;
-        for (int j = 0; j < n; ++j) row += w.H[(size_t)i * n + j] * w.scale[j] * w.step[j];
-        acc += -w.step[i] * w.scale[i] * w.g[i] - 0.5 * w.step[i] * w.scale[i] * row;
+        const double y = w.rhs[i];
+        acc += 0.5 * (y * w.scale[i] * w.g[i] + (w.diag[i] / radius) * y * y);
       }
       mcc = block_sum(acc, red);
     }

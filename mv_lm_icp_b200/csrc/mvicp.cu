@@ -423,18 +423,16 @@ int mvicp_get_graph(mvicp_ctx* c, int32_t* E, int32_t* src, int32_t* dst) {
 template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   const int E = c->E;
   edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
-  CU(cudaMemsetAsync(c->d_count.p, 0, sizeof(unsigned long long) * E, c->stream));
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
   if (c->n_knn_tiles)
     knn_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
         c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
-        c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr,
-        c->d_count.as<unsigned long long>(), (double)thresh);
+        c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh);
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);
   // exact median -> weight
-  select_init_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_count.as<unsigned long long>(), c->d_sel.as<SelState>(), E);
+  select_init_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_sel.as<SelState>(), E);
   c->stats.kernel_launches += 1;
   const int shifts[6] = {53, 42, 31, 20, 9, 0}, nbits[6] = {11, 11, 11, 11, 11, 9};
   for (int p = 0; p < 6; ++p) {
@@ -442,8 +440,9 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
       select_hist_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(
           c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len, c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
           c->d_sel.as<SelState>(), shifts[p], nbits[p], c->d_hist.as<unsigned int>());
-    select_pick_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_hist.as<unsigned int>(), shifts[p], p == 5,
-                                                         c->d_weight.as<float>(), c->d_median.as<double>());
+    select_pick_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_hist.as<unsigned int>(), shifts[p], p == 0, p == 5,
+                                                         c->d_weight.as<float>(), c->d_median.as<double>(),
+                                                         c->d_count.as<unsigned long long>());
     c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
   }
   CU(cudaEventRecord(c->ev[2], c->stream));
@@ -551,7 +550,8 @@ static int prepare_lm(mvicp_ctx* c, int n) {
   RET(c->d_x.reserve(sizeof(double) * 7 * M)); RET(c->d_cand.reserve(sizeof(double) * 7 * M));
   RET(c->d_Rt.reserve(sizeof(Rt) * M)); RET(c->d_K.reserve(sizeof(double) * 36 * M));
   RET(c->d_col.reserve(sizeof(int32_t) * M));
-  RET(c->d_H.reserve(sizeof(double) * n * n)); RET(c->d_Hc.reserve(sizeof(double) * n * n)); RET(c->d_L.reserve(sizeof(double) * n * n));
+  RET(c->d_H.reserve(sizeof(double) * n * n)); RET(c->d_Hc.reserve(sizeof(double) * n * n));
+  RET(c->d_L.reserve(sizeof(double) * (size_t)(n + 1) * (n | 1)));
   RET(c->d_g.reserve(sizeof(double) * n)); RET(c->d_gc.reserve(sizeof(double) * n)); RET(c->d_scale.reserve(sizeof(double) * n));
   RET(c->d_diag.reserve(sizeof(double) * n)); RET(c->d_rhs.reserve(sizeof(double) * n)); RET(c->d_step.reserve(sizeof(double) * n));
   RET(c->d_Qs.reserve(sizeof(double) * 36 * E)); RET(c->d_AQ.reserve(sizeof(double) * 36 * E));
@@ -647,10 +647,11 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   w.step = c->d_step.as<double>(); w.Qs = c->d_Qs.as<double>(); w.AQ = c->d_AQ.as<double>(); w.Hcan = c->d_Hcan.as<double>();
   w.T1 = c->d_T1.as<double>(); w.Hp = c->d_Hp.as<double>();
   w.gp = c->d_gp.as<double>(); w.poses16 = c->d_poses.as<double>();
-  const size_t l_bytes = sizeof(double) * (size_t)n * n;
-  w.l_in_smem = l_bytes <= 200 * 1024 ? 1 : 0;
-  const size_t dyn = w.l_in_smem ? l_bytes : 0;
-  CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const size_t l_bytes = sizeof(double) * (size_t)(n + 1) * (n | 1);
+  const size_t vec_bytes = sizeof(double) * 2 * (size_t)(n + 1);
+  w.l_in_smem = (l_bytes + vec_bytes) <= 220 * 1024 ? 1 : 0;
+  const size_t dyn = vec_bytes + (w.l_in_smem ? l_bytes : 0);
+  CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
   CU(cudaEventRecord(c->ev[3], c->stream));
   lm_init_kernel<<<(M + 63) / 64, 64, 0, c->stream>>>(w);

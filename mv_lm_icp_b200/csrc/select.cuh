@@ -20,10 +20,10 @@ struct SelState {            // one per edge
   unsigned long long count;  // inliers of the edge
 };
 
-__global__ void select_init_kernel(const unsigned long long* __restrict__ edge_count, SelState* __restrict__ st, int n_edges) {
+__global__ void select_init_kernel(SelState* __restrict__ st, int n_edges) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
-  st[e].prefix = 0ull; st[e].count = edge_count[e]; st[e].rank = edge_count[e] / 2;   // dists.size() / 2
+  st[e].prefix = 0ull; st[e].count = 0ull; st[e].rank = 0ull;   // count / rank are set by the first pick (histogram total)
 }
 
 // hist[e][bin] += #inliers of the tile whose high bits equal the edge's prefix and whose digit is `bin`
@@ -54,8 +54,8 @@ select_hist_kernel(const EdgeDev* __restrict__ edges, const Tile* __restrict__ t
 // one block per edge: find the bin holding the wanted rank, extend the prefix, clear the histogram.
 // On the last pass the prefix is the exact bit pattern of the median squared distance -> weight.
 __global__ void __launch_bounds__(SEL_THREADS)
-select_pick_kernel(SelState* __restrict__ st, unsigned int* __restrict__ hist, int shift, int last,
-                   float* __restrict__ weight, double* __restrict__ median) {
+select_pick_kernel(SelState* __restrict__ st, unsigned int* __restrict__ hist, int shift, int first, int last,
+                   float* __restrict__ weight, double* __restrict__ median, unsigned long long* __restrict__ edge_count) {
   const int e = blockIdx.x;
   unsigned int* h = hist + (size_t)e * SEL_BINS;
   __shared__ unsigned int part[SEL_THREADS];
@@ -67,6 +67,10 @@ select_pick_kernel(SelState* __restrict__ st, unsigned int* __restrict__ hist, i
   if (threadIdx.x == 0) { s_bin = -1; s_before = 0; }
   __syncthreads();
   if (threadIdx.x == 0) {   // 256 partial sums: serial scan is fine (once per edge per pass)
+    if (first) {   // the first histogram covers every inlier: its total is dists.size(), the wanted rank size()/2
+      unsigned long long tot = 0; for (int t = 0; t < SEL_THREADS; ++t) tot += part[t];
+      st[e].count = tot; st[e].rank = tot / 2; edge_count[e] = tot;
+    }
     unsigned long long acc = 0; const unsigned long long rank = st[e].rank;
     for (int t = 0; t < SEL_THREADS; ++t) {
       if (rank < acc + part[t]) { s_bin = t; s_before = acc; break; }
