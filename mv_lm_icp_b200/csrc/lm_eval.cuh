@@ -29,6 +29,17 @@ namespace mv {
 
 enum { COST_P2P = 0, COST_P2PLANE = 1, COST_MIXED = 2 };
 
+template <bool F32> __device__ __forceinline__ typename Rec<F32>::type rec_load(const void* base, int64_t i);
+template <> __device__ __forceinline__ float4 rec_load<true>(const void* base, int64_t i) {
+  return __ldg(reinterpret_cast<const float4*>(base) + i);
+}
+template <> __device__ __forceinline__ double4a rec_load<false>(const void* base, int64_t i) {
+  const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double4a*>(base) + i);
+  const double2 a = __ldg(p), b = __ldg(p + 1);
+  double4a r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+  return r;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -37,7 +48,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // partial[tile][NBLK]: layout BLK_* of types.cuh
 template <bool F32, int COST>
-__global__ void __launch_bounds__(EVAL_THREADS)
+__global__ void __launch_bounds__(EVAL_THREADS, 2)
 lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
                int tile_len, const int32_t* __restrict__ corr, const Rt* __restrict__ frame_Rt,
                const float* __restrict__ weight, int robust, double* __restrict__ partial) {
@@ -72,61 +83,77 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
          swpq[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // point-to-point moments
 
   const int end = min(t.start + tile_len, e.n_src);
-  for (int k = t.start + threadIdx.x; k < end; k += EVAL_THREADS) {
-    const int c = __ldg(corr + e.off + k);
-    if (c < 0) continue;
-    double px, py, pz, qx, qy, qz; int dummy;
-    Rec<F32>::load(fs.pts_o, k, px, py, pz, dummy);
-    Rec<F32>::load(fd.pts_o, c, qx, qy, qz, dummy);
-    const double x0 = R[0] * px + R[1] * py + R[2] * pz + tr[0];
-    const double x1 = R[3] * px + R[4] * py + R[5] * pz + tr[1];
-    const double x2 = R[6] * px + R[7] * py + R[8] * pz + tr[2];
-    const double d0 = x0 - qx, d1 = x1 - qy, d2 = x2 - qz;
-    if (COST == COST_P2PLANE || COST == COST_MIXED) {
-      double nx, ny, nz;
-      Rec<F32>::load(fd.nor_o, c, nx, ny, nz, dummy);
-      const double r = d0 * nx + d1 * ny + d2 * nz;
-      const double s = r * r;
-      double w = 1.0;
-      if (robust) { const double tt = sqrt(1.0 + s * cc); w = 1.0 / tt; cost += bb * (tt - 1.0); }
-      else cost += 0.5 * s;
-      double a[6];
-      a[0] = R[0] * nx + R[3] * ny + R[6] * nz;   // m = R_rel^T n
-      a[1] = R[1] * nx + R[4] * ny + R[7] * nz;
-      a[2] = R[2] * nx + R[5] * ny + R[8] * nz;
-      a[3] = py * a[2] - pz * a[1];               // p x m
-      a[4] = pz * a[0] - px * a[2];
-      a[5] = px * a[1] - py * a[0];
-      const double wr = w * r;
-      int idx = 0;
+  typedef typename Rec<F32>::type rec_t;
+  constexpr int U = F32 ? 4 : 2;   // slots in flight per thread: all index loads, then all gathers, then the math
+  for (int k0 = t.start + threadIdx.x; k0 < end; k0 += U * EVAL_THREADS) {
+    int cidx[U];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double wa = w * a[i];
-        g[i] += wr * a[i];
-#pragma unroll
-        for (int j = i; j < 6; ++j) A[idx++] += wa * a[j];
-      }
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * EVAL_THREADS;
+      cidx[u] = (k < end) ? __ldg(corr + e.off + k) : -1;
     }
-    if (COST == COST_P2P || COST == COST_MIXED) {
-      const double s = d0 * d0 + d1 * d1 + d2 * d2;
-      double w = 1.0;
-      if (robust) { const double tt = sqrt(1.0 + s * cc); w = 1.0 / tt; cost += bb * (tt - 1.0); }
-      else cost += 0.5 * s;
-      const double u0 = R[0] * d0 + R[3] * d1 + R[6] * d2;   // u = R_rel^T d
-      const double u1 = R[1] * d0 + R[4] * d1 + R[7] * d2;
-      const double u2 = R[2] * d0 + R[5] * d1 + R[8] * d2;
-      g[0] += w * u0; g[1] += w * u1; g[2] += w * u2;
-      g[3] += w * (py * u2 - pz * u1); g[4] += w * (pz * u0 - px * u2); g[5] += w * (px * u1 - py * u0);
-      sw += w;
-      const double wx = w * px, wy = w * py, wz = w * pz;
-      const double vx = w * qx, vy = w * qy, vz = w * qz;
-      swp[0] += wx; swp[1] += wy; swp[2] += wz;
-      swq[0] += vx; swq[1] += vy; swq[2] += vz;
-      swpp[0] += wx * px; swpp[1] += wx * py; swpp[2] += wx * pz; swpp[3] += wy * py; swpp[4] += wy * pz; swpp[5] += wz * pz;
-      swqq[0] += vx * qx; swqq[1] += vx * qy; swqq[2] += vx * qz; swqq[3] += vy * qy; swqq[4] += vy * qz; swqq[5] += vz * qz;
-      swpq[0] += wx * qx; swpq[1] += wx * qy; swpq[2] += wx * qz;
-      swpq[3] += wy * qx; swpq[4] += wy * qy; swpq[5] += wy * qz;
-      swpq[6] += wz * qx; swpq[7] += wz * qy; swpq[8] += wz * qz;
+    rec_t P[U], Q[U], Nn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (cidx[u] >= 0) {
+        P[u] = rec_load<F32>(fs.pts_o, k0 + u * EVAL_THREADS);
+        Q[u] = rec_load<F32>(fd.pts_o, cidx[u]);
+        if (COST != COST_P2P) Nn[u] = rec_load<F32>(fd.nor_o, cidx[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (cidx[u] < 0) continue;
+      const double px = (double)P[u].x, py = (double)P[u].y, pz = (double)P[u].z;
+      const double qx = (double)Q[u].x, qy = (double)Q[u].y, qz = (double)Q[u].z;
+      const double x0 = R[0] * px + R[1] * py + R[2] * pz + tr[0];
+      const double x1 = R[3] * px + R[4] * py + R[5] * pz + tr[1];
+      const double x2 = R[6] * px + R[7] * py + R[8] * pz + tr[2];
+      const double d0 = x0 - qx, d1 = x1 - qy, d2 = x2 - qz;
+      if (COST == COST_P2PLANE || COST == COST_MIXED) {
+        const double nx = (double)Nn[u].x, ny = (double)Nn[u].y, nz = (double)Nn[u].z;
+        const double r = d0 * nx + d1 * ny + d2 * nz;
+        const double s = r * r;
+        double w = 1.0;
+        if (robust) { const double arg = 1.0 + s * cc; w = rsqrt(arg); cost += bb * (arg * w - 1.0); }
+        else cost += 0.5 * s;
+        double a[6];
+        a[0] = R[0] * nx + R[3] * ny + R[6] * nz;   // m = R_rel^T n
+        a[1] = R[1] * nx + R[4] * ny + R[7] * nz;
+        a[2] = R[2] * nx + R[5] * ny + R[8] * nz;
+        a[3] = py * a[2] - pz * a[1];               // p x m
+        a[4] = pz * a[0] - px * a[2];
+        a[5] = px * a[1] - py * a[0];
+        const double wr = w * r;
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double wa = w * a[i];
+          g[i] += wr * a[i];
+#pragma unroll
+          for (int j = i; j < 6; ++j) A[idx++] += wa * a[j];
+        }
+      }
+      if (COST == COST_P2P || COST == COST_MIXED) {
+        const double s = d0 * d0 + d1 * d1 + d2 * d2;
+        double w = 1.0;
+        if (robust) { const double arg = 1.0 + s * cc; w = rsqrt(arg); cost += bb * (arg * w - 1.0); }
+        else cost += 0.5 * s;
+        const double u0 = R[0] * d0 + R[3] * d1 + R[6] * d2;   // u = R_rel^T d
+        const double u1 = R[1] * d0 + R[4] * d1 + R[7] * d2;
+        const double u2 = R[2] * d0 + R[5] * d1 + R[8] * d2;
+        g[0] += w * u0; g[1] += w * u1; g[2] += w * u2;
+        g[3] += w * (py * u2 - pz * u1); g[4] += w * (pz * u0 - px * u2); g[5] += w * (px * u1 - py * u0);
+        sw += w;
+        const double wx = w * px, wy = w * py, wz = w * pz;
+        const double vx = w * qx, vy = w * qy, vz = w * qz;
+        swp[0] += wx; swp[1] += wy; swp[2] += wz;
+        swq[0] += vx; swq[1] += vy; swq[2] += vz;
+        swpp[0] += wx * px; swpp[1] += wx * py; swpp[2] += wx * pz; swpp[3] += wy * py; swpp[4] += wy * pz; swpp[5] += wz * pz;
+        swqq[0] += vx * qx; swqq[1] += vx * qy; swqq[2] += vx * qz; swqq[3] += vy * qy; swqq[4] += vy * qz; swqq[5] += vz * qz;
+        swpq[0] += wx * qx; swpq[1] += wx * qy; swpq[2] += wx * qz;
+        swpq[3] += wy * qx; swpq[4] += wy * qy; swpq[5] += wy * qz;
+        swpq[6] += wz * qx; swpq[7] += wz * qy; swpq[8] += wz * qz;
+      }
     }
   }
   // block reduction: warp shuffles, then one value per warp through shared memory, fixed order

@@ -37,6 +37,7 @@ struct LmWork {
   // block-sparse gather lists (host-built, deterministic order)
   const int32_t* hb_ptr; const int32_t* hb_row; const int32_t* hb_col; const int32_t* hc_edge; const int32_t* hc_sub; int32_t n_hblocks;
   const int32_t* gb_ptr; const int32_t* gc_edge; const int32_t* gc_side;   // per frame
+  const int32_t* rlast; const int32_t* rfirst;   // envelope of the normal matrix: last row touching column j / first column of row r
   double *H, *g, *Hc, *gc, *scale, *diag, *Lg, *rhs, *step, *Qs, *AQ, *Hcan, *T1, *Hp, *gp;
   double* poses16;
   int32_t l_in_smem;
@@ -88,22 +89,29 @@ __global__ void lm_init_kernel(LmWork w) {
 // Right-looking factorisation; treating the rhs as an extra row performs the forward substitution for free.  Each
 // scaled column is stashed contiguously (colj) so the rank-1 update reads conflict-free; the diagonal of the factor
 // goes to dg.  The back substitution runs in one warp (shuffle-free, __syncwarp only).  Solution returned in y[0..n).
-__device__ bool chol_solve(double* L, int ld, int n, double* colj, double* dg, double* y) {
+__device__ bool chol_solve(double* L, int ld, int n, double* colj, double* dg, double* y, const int32_t* __restrict__ rlast,
+                           const int32_t* __restrict__ rfirst) {
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   for (int j = 0; j < n; ++j) {
     __syncthreads();
     const double d = L[(size_t)j * ld + j];
     if (!(d > 0.0) || !isfinite(d)) return false;     // uniform: every thread reads the same value
     const double sd = sqrt(d), inv = 1.0 / sd;
-    for (int r = j + tid; r <= n; r += T) {
+    // rows beyond rlast[j] are structurally zero in column j (envelope of the block-sparse matrix: the factor fills
+    // only inside each row's profile), so the rank-1 update is confined to rows/cols (j, rlast[j]] plus the rhs row n
+    const int rl = rlast[j];
+    for (int r = j + tid; r <= rl; r += T) {
       if (r == j) { colj[j] = sd; dg[j] = sd; }
       else { const double v = L[(size_t)r * ld + j] * inv; L[(size_t)r * ld + j] = v; colj[r] = v; }
     }
+    if (tid == 0) { const double v = L[(size_t)n * ld + j] * inv; L[(size_t)n * ld + j] = v; colj[n] = v; }
     __syncthreads();
-    for (int r = j + 1 + wid; r <= n; r += nw) {
+    const int nrows = rl - j + 1;   // rows j+1..rl and the rhs row
+    for (int q = wid; q < nrows; q += nw) {
+      const int r = (q == nrows - 1) ? n : j + 1 + q;
       const double lr = colj[r];
       double* row = L + (size_t)r * ld;
-      const int cend = min(r, n - 1);
+      const int cend = min(r, rl);
       for (int c = j + 1 + lane; c <= cend; c += 32) row[c] -= lr * colj[c];
     }
   }
@@ -116,7 +124,7 @@ __device__ bool chol_solve(double* L, int ld, int n, double* colj, double* dg, d
       __syncwarp();
       if (lane == 0) y[j] = yj;
       const double* row = L + (size_t)j * ld;
-      for (int i = lane; i < j; i += 32) y[i] -= row[i] * yj;
+      for (int i = rfirst[j] + lane; i < j; i += 32) y[i] -= row[i] * yj;
       __syncwarp();
     }
   }
@@ -375,7 +383,7 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     }
     for (int j = tid; j < n; j += T) L[(size_t)n * ldl + j] = w.scale[j] * w.g[j];
     __syncthreads();
-    bool ok = chol_solve(L, ldl, n, colj, dg, w.rhs);
+    bool ok = chol_solve(L, ldl, n, colj, dg, w.rhs, w.rlast, w.rfirst);
     double bad = 0.0;
     if (ok) for (int j = tid; j < n; j += T) if (!isfinite(w.rhs[j])) bad = 1.0;
     bad = block_sum(bad, red);

@@ -83,7 +83,7 @@ struct mvicp_ctx {
   std::vector<float> h_weight; std::vector<unsigned long long> h_count;
   // LM
   DevBuf d_state, d_x, d_cand, d_Rt, d_K, d_col, d_H, d_g, d_Hc, d_gc, d_scale, d_diag, d_L, d_rhs, d_step,
-      d_Qs, d_AQ, d_Hcan, d_T1, d_Hp, d_gp, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather;
+      d_Qs, d_AQ, d_Hcan, d_T1, d_Hp, d_gp, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst;
   int n_free = 0, n_hblocks = 0;
   std::vector<int32_t> h_col;
   int32_t* h_done = nullptr;   // pinned
@@ -231,7 +231,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_blocks, &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_Qs, &c->d_AQ, &c->d_Hcan, &c->d_T1, &c->d_Hp, &c->d_gp,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -620,6 +620,14 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     }
   for (int f = 0; f < M; ++f) { for (auto& pr : gl[f]) { gc_edge.push_back(pr.first); gc_side.push_back(pr.second); } gb_ptr.push_back((int32_t)gc_edge.size()); }
   c->n_hblocks = (int)hb_row.size();
+  // envelope: first structurally non-zero column of every row, and the last row that reaches column j
+  std::vector<int32_t> rfirst(n), rlast(n);
+  for (int r = 0; r < n; ++r) rfirst[r] = (r / 6) * 6;
+  for (int b = 0; b < c->n_hblocks; ++b)
+    if (hb_col[b] < hb_row[b]) for (int i = 0; i < 6; ++i) rfirst[hb_row[b] + i] = std::min(rfirst[hb_row[b] + i], hb_col[b]);
+  for (int j = 0; j < n; ++j) { rlast[j] = j; }
+  for (int r = 0; r < n; ++r) for (int j = rfirst[r]; j <= r; ++j) rlast[j] = std::max(rlast[j], r);
+  for (int j = 1; j < n; ++j) rlast[j] = std::max(rlast[j], rlast[j - 1]);   // monotone (fill-in stays inside)
   auto up = [&](DevBuf& b, const std::vector<int32_t>& v) -> int {
     RET(b.reserve(sizeof(int32_t) * std::max<size_t>(1, v.size())));
     if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, c->stream));
@@ -628,6 +636,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   RET(up(c->d_hb_ptr, hb_ptr)); RET(up(c->d_hb_row, hb_row)); RET(up(c->d_hb_col, hb_col)); RET(up(c->d_hc_edge, hc_edge));
   RET(up(c->d_hc_sub, hc_sub)); RET(up(c->d_gb_ptr, gb_ptr)); RET(up(c->d_gc_edge, gc_edge)); RET(up(c->d_gc_side, gc_side));
   RET(up(c->d_col, c->h_col));
+  RET(up(c->d_rlast, rlast)); RET(up(c->d_rfirst, rfirst));
 
   LmState st; std::memset(&st, 0, sizeof st);
   st.opt = opt; st.param = param; st.cost_kind = cost; st.robust = robust ? 1 : 0; st.M = M; st.E = E; st.F = n / 6; st.n = n;
@@ -641,6 +650,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   w.col = c->d_col.as<int32_t>();
   w.hb_ptr = c->d_hb_ptr.as<int32_t>(); w.hb_row = c->d_hb_row.as<int32_t>(); w.hb_col = c->d_hb_col.as<int32_t>();
   w.hc_edge = c->d_hc_edge.as<int32_t>(); w.hc_sub = c->d_hc_sub.as<int32_t>(); w.n_hblocks = c->n_hblocks;
+  w.rlast = c->d_rlast.as<int32_t>(); w.rfirst = c->d_rfirst.as<int32_t>();
   w.gb_ptr = c->d_gb_ptr.as<int32_t>(); w.gc_edge = c->d_gc_edge.as<int32_t>(); w.gc_side = c->d_gc_side.as<int32_t>();
   w.H = c->d_H.as<double>(); w.g = c->d_g.as<double>(); w.Hc = c->d_Hc.as<double>(); w.gc = c->d_gc.as<double>();
   w.scale = c->d_scale.as<double>(); w.diag = c->d_diag.as<double>(); w.Lg = c->d_L.as<double>(); w.rhs = c->d_rhs.as<double>();
