@@ -51,7 +51,8 @@ template <bool F32, int COST>
 __global__ void __launch_bounds__(EVAL_THREADS, 2)
 lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
                int tile_len, const int32_t* __restrict__ corr, const Rt* __restrict__ frame_Rt,
-               const float* __restrict__ weight, int robust, double* __restrict__ partial) {
+               const float* __restrict__ weight, int robust, double* __restrict__ partial, const int* __restrict__ done_flag) {
+  if (*done_flag) return;   // issued speculatively after the solve terminated
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ double sRel[12];
@@ -191,7 +192,8 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
 
 // blocks[e][NBLK] = sum of the edge's tile partials in tile order (deterministic); zero for edges not owned.
 __global__ void lm_reduce_kernel(const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
-                                 double* __restrict__ blocks, int nused) {
+                                 double* __restrict__ blocks, int nused, const int* __restrict__ done_flag) {
+  if (*done_flag) return;
   const int e = blockIdx.x, j = threadIdx.x;
   if (j >= NBLK) return;
   if (j >= nused) { blocks[(size_t)e * NBLK + j] = 0.0; return; }

@@ -86,7 +86,10 @@ struct mvicp_ctx {
       d_Qs, d_AQ, d_Hcan, d_T1, d_Hp, d_gp, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst;
   int n_free = 0, n_hblocks = 0;
   std::vector<int32_t> h_col;
-  int32_t* h_done = nullptr;   // pinned
+  int32_t* h_done = nullptr;   // pinned ring of termination flags
+  void* h_state = nullptr;     // pinned staging of LmState
+  std::vector<cudaEvent_t> iter_ev;
+  std::vector<uint8_t> lm_key; uint32_t graph_gen = 0;
   // stats
   mvicp_stats stats{};
   cudaEvent_t ev[8]{};
@@ -215,7 +218,8 @@ int mvicp_create(const mvicp_config* cfg, mvicp_ctx** out) {
   if (cfg && cfg->stream) c->stream = (cudaStream_t)cfg->stream;
   else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
-  CU(cudaMallocHost((void**)&c->h_done, 64));
+  CU(cudaMallocHost((void**)&c->h_done, sizeof(int32_t) * 256));
+  CU(cudaMallocHost(&c->h_state, sizeof(LmState)));
   *out = c;
   return MVICP_OK;
 }
@@ -236,6 +240,8 @@ void mvicp_destroy(mvicp_ctx* c) {
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
   if (c->h_done) cudaFreeHost(c->h_done);
+  if (c->h_state) cudaFreeHost(c->h_state);
+  for (auto& ev : c->iter_ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -379,6 +385,7 @@ static int rebuild_work(mvicp_ctx* c) {
   CU(cudaMemset(c->d_corr.p, 0xff, sizeof(int32_t) * off));   // ~0 = "no inlier, candidate 0"
   c->h_weight.assign(E, 0.f); c->h_count.assign(E, 0ull);
   c->have_corr = false;
+  ++c->graph_gen;
   return MVICP_OK;
 }
 
@@ -561,13 +568,13 @@ static int prepare_lm(mvicp_ctx* c, int n) {
 }
 
 }  // extern "C"
-template <bool F32> static void launch_eval(mvicp_ctx* c, int cost, int robust) {
+template <bool F32> static void launch_eval(mvicp_ctx* c, int cost, int robust, const int* done_flag) {
   const int nt = c->n_eval_tiles;
   if (!nt) return;
 #define MV_EVAL(COSTK)                                                                                           \
   lm_eval_kernel<F32, COSTK><<<nt, EVAL_THREADS, 0, c->stream>>>(                                                \
       c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
-      c->d_corr.as<int32_t>(), c->d_Rt.as<Rt>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>())
+      c->d_corr.as<int32_t>(), c->d_Rt.as<Rt>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag)
   if (cost == COST_P2P) MV_EVAL(COST_P2P); else if (cost == COST_P2PLANE) MV_EVAL(COST_P2PLANE); else MV_EVAL(COST_MIXED);
 #undef MV_EVAL
 }
@@ -596,53 +603,59 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     if (want != c->h_edges[e].owned) stale = true;
   }
   if (stale) return fail(MVICP_ERR_STATE, "fixed flags changed after mvicp_set_graph: call mvicp_set_graph again");
+  // the gather lists / envelope depend only on the graph and the fixed flags: build and upload them when those change
+  std::vector<uint8_t> key(c->fixed); key.push_back((uint8_t)(c->graph_gen & 0xff)); key.push_back((uint8_t)((c->graph_gen >> 8) & 0xff));
+  if (key != c->lm_key) {
   RET(prepare_lm(c, n));
-  // block-sparse gather lists
-  std::vector<std::vector<std::pair<int, int>>> blk((size_t)M * M);
-  std::vector<std::vector<std::pair<int, int>>> gl(M);
-  for (int e = 0; e < E; ++e) {
-    const int s = c->h_edges[e].src, k = c->h_edges[e].dst;
-    if (c->fixed[s]) continue;
-    blk[(size_t)s * M + s].push_back({e, 0}); gl[s].push_back({e, 0});
-    if (!c->fixed[k]) {
-      blk[(size_t)s * M + k].push_back({e, 1}); blk[(size_t)k * M + s].push_back({e, 2}); blk[(size_t)k * M + k].push_back({e, 3});
-      gl[k].push_back({e, 1});
+    // block-sparse gather lists
+    std::vector<std::vector<std::pair<int, int>>> blk((size_t)M * M);
+    std::vector<std::vector<std::pair<int, int>>> gl(M);
+    for (int e = 0; e < E; ++e) {
+      const int s = c->h_edges[e].src, k = c->h_edges[e].dst;
+      if (c->fixed[s]) continue;
+      blk[(size_t)s * M + s].push_back({e, 0}); gl[s].push_back({e, 0});
+      if (!c->fixed[k]) {
+        blk[(size_t)s * M + k].push_back({e, 1}); blk[(size_t)k * M + s].push_back({e, 2}); blk[(size_t)k * M + k].push_back({e, 3});
+        gl[k].push_back({e, 1});
+      }
     }
-  }
-  std::vector<int32_t> hb_ptr{0}, hb_row, hb_col, hc_edge, hc_sub, gb_ptr{0}, gc_edge, gc_side;
-  for (int r = 0; r < M; ++r)
-    for (int q = 0; q < M; ++q) {
-      const auto& l = blk[(size_t)r * M + q];
-      if (l.empty()) continue;
-      hb_row.push_back(c->h_col[r]); hb_col.push_back(c->h_col[q]);
-      for (auto& pr : l) { hc_edge.push_back(pr.first); hc_sub.push_back(pr.second); }
-      hb_ptr.push_back((int32_t)hc_edge.size());
-    }
-  for (int f = 0; f < M; ++f) { for (auto& pr : gl[f]) { gc_edge.push_back(pr.first); gc_side.push_back(pr.second); } gb_ptr.push_back((int32_t)gc_edge.size()); }
-  c->n_hblocks = (int)hb_row.size();
-  // envelope: first structurally non-zero column of every row, and the last row that reaches column j
-  std::vector<int32_t> rfirst(n), rlast(n);
-  for (int r = 0; r < n; ++r) rfirst[r] = (r / 6) * 6;
-  for (int b = 0; b < c->n_hblocks; ++b)
-    if (hb_col[b] < hb_row[b]) for (int i = 0; i < 6; ++i) rfirst[hb_row[b] + i] = std::min(rfirst[hb_row[b] + i], hb_col[b]);
-  for (int j = 0; j < n; ++j) { rlast[j] = j; }
-  for (int r = 0; r < n; ++r) for (int j = rfirst[r]; j <= r; ++j) rlast[j] = std::max(rlast[j], r);
-  for (int j = 1; j < n; ++j) rlast[j] = std::max(rlast[j], rlast[j - 1]);   // monotone (fill-in stays inside)
-  auto up = [&](DevBuf& b, const std::vector<int32_t>& v) -> int {
-    RET(b.reserve(sizeof(int32_t) * std::max<size_t>(1, v.size())));
-    if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, c->stream));
-    return MVICP_OK;
-  };
-  RET(up(c->d_hb_ptr, hb_ptr)); RET(up(c->d_hb_row, hb_row)); RET(up(c->d_hb_col, hb_col)); RET(up(c->d_hc_edge, hc_edge));
-  RET(up(c->d_hc_sub, hc_sub)); RET(up(c->d_gb_ptr, gb_ptr)); RET(up(c->d_gc_edge, gc_edge)); RET(up(c->d_gc_side, gc_side));
-  RET(up(c->d_col, c->h_col));
-  RET(up(c->d_rlast, rlast)); RET(up(c->d_rfirst, rfirst));
+    std::vector<int32_t> hb_ptr{0}, hb_row, hb_col, hc_edge, hc_sub, gb_ptr{0}, gc_edge, gc_side;
+    for (int r = 0; r < M; ++r)
+      for (int q = 0; q < M; ++q) {
+        const auto& l = blk[(size_t)r * M + q];
+        if (l.empty()) continue;
+        hb_row.push_back(c->h_col[r]); hb_col.push_back(c->h_col[q]);
+        for (auto& pr : l) { hc_edge.push_back(pr.first); hc_sub.push_back(pr.second); }
+        hb_ptr.push_back((int32_t)hc_edge.size());
+      }
+    for (int f = 0; f < M; ++f) { for (auto& pr : gl[f]) { gc_edge.push_back(pr.first); gc_side.push_back(pr.second); } gb_ptr.push_back((int32_t)gc_edge.size()); }
+    c->n_hblocks = (int)hb_row.size();
+    // envelope: first structurally non-zero column of every row, and the last row that reaches column j
+    std::vector<int32_t> rfirst(n), rlast(n);
+    for (int r = 0; r < n; ++r) rfirst[r] = (r / 6) * 6;
+    for (int b = 0; b < c->n_hblocks; ++b)
+      if (hb_col[b] < hb_row[b]) for (int i = 0; i < 6; ++i) rfirst[hb_row[b] + i] = std::min(rfirst[hb_row[b] + i], hb_col[b]);
+    for (int j = 0; j < n; ++j) { rlast[j] = j; }
+    for (int r = 0; r < n; ++r) for (int j = rfirst[r]; j <= r; ++j) rlast[j] = std::max(rlast[j], r);
+    for (int j = 1; j < n; ++j) rlast[j] = std::max(rlast[j], rlast[j - 1]);   // monotone (fill-in stays inside)
+    auto up = [&](DevBuf& b, const std::vector<int32_t>& v) -> int {
+      RET(b.reserve(sizeof(int32_t) * std::max<size_t>(1, v.size())));
+      if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice, c->stream));
+      return MVICP_OK;
+    };
+    RET(up(c->d_hb_ptr, hb_ptr)); RET(up(c->d_hb_row, hb_row)); RET(up(c->d_hb_col, hb_col)); RET(up(c->d_hc_edge, hc_edge));
+    RET(up(c->d_hc_sub, hc_sub)); RET(up(c->d_gb_ptr, gb_ptr)); RET(up(c->d_gc_edge, gc_edge)); RET(up(c->d_gc_side, gc_side));
+    RET(up(c->d_col, c->h_col));
+    RET(up(c->d_rlast, rlast)); RET(up(c->d_rfirst, rfirst));
 
+    CU(cudaStreamSynchronize(c->stream));   // the host vectors above must outlive their copies
+    c->lm_key = key;
+  }
   LmState st; std::memset(&st, 0, sizeof st);
   st.opt = opt; st.param = param; st.cost_kind = cost; st.robust = robust ? 1 : 0; st.M = M; st.E = E; st.F = n / 6; st.n = n;
   st.G = ambient_size(param); st.radius = opt.initial_trust_region_radius; st.decrease_factor = 2.0;
-  CU(cudaMemcpyAsync(c->d_state.p, &st, sizeof st, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));   // host vectors above go out of scope only after the copies landed
+  std::memcpy(c->h_state, &st, sizeof st);   // pinned staging: no synchronisation needed before the kernels
+  CU(cudaMemcpyAsync(c->d_state.p, c->h_state, sizeof st, cudaMemcpyHostToDevice, c->stream));
 
   LmWork w{};
   w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.blocks = c->d_blocks.as<double>();
@@ -666,25 +679,38 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   CU(cudaEventRecord(c->ev[3], c->stream));
   lm_init_kernel<<<(M + 63) / 64, 64, 0, c->stream>>>(w);
   c->stats.kernel_launches += 1;
-  int evals = 0;
+  // The loop is pipelined one iteration deep: iteration i+1 is enqueued before the host learns whether iteration i
+  // terminated, so the GPU never waits for the host; kernels of an iteration issued after termination exit at once.
   const int max_evals = opt.max_num_iterations + 2;
+  const int ring = 8;   // at most two iterations are in flight
+  while ((int)c->iter_ev.size() < ring) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->iter_ev.push_back(e); }
   c->eval_ev_used = 0;
-  while (true) {
+  int issued = 0, seen = 0;
+  const int* done_flag = &w.S->done;
+  auto issue = [&]() -> int {
     if ((int)c->eval_ev.size() < c->eval_ev_used + 2) { cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); c->eval_ev.push_back(a); c->eval_ev.push_back(b); }
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used], c->stream));
-    if (c->f32) launch_eval<true>(c, cost, st.robust); else launch_eval<false>(c, cost, st.robust);
+    if (c->f32) launch_eval<true>(c, cost, st.robust, done_flag); else launch_eval<false>(c, cost, st.robust, done_flag);
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used + 1], c->stream));
     c->eval_ev_used += 2;
     lm_reduce_kernel<<<E, 64, 0, c->stream>>>(c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(), c->d_blocks.as<double>(),
-                                             cost == COST_P2PLANE ? NBLK_PLANE : NBLK);
+                                             cost == COST_P2PLANE ? NBLK_PLANE : NBLK, done_flag);
     if (c->comm && c->world > 1)
       NC(ncclAllReduce(c->d_blocks.p, c->d_blocks.p, (size_t)NBLK * E, ncclDouble, ncclSum, c->comm, c->stream));
     lm_step_kernel<<<1, STEP_THREADS, dyn, c->stream>>>(w);
     c->stats.kernel_launches += (c->n_eval_tiles ? 1 : 0) + 2;
-    ++evals;
-    CU(cudaMemcpyAsync(c->h_done, &w.S->done, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (*c->h_done || evals > max_evals) break;
+    CU(cudaMemcpyAsync(c->h_done + (issued % ring), done_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->iter_ev[issued % ring], c->stream));
+    ++issued;
+    return MVICP_OK;
+  };
+  RET(issue());
+  while (true) {
+    if (issued - seen < 2 && issued <= max_evals) RET(issue());
+    CU(cudaEventSynchronize(c->iter_ev[seen % ring]));
+    const bool fin = c->h_done[seen % ring] != 0;
+    ++seen;
+    if (fin || seen > max_evals) break;
   }
   // sharded runs: every rank holds identical poses (identical solve on identical all-reduced blocks); the
   // owners' copies are gathered anyway so that a caller never sees rank-dependent state.
@@ -705,8 +731,9 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     }
   }
   CU(cudaEventRecord(c->ev[4], c->stream));
-  CU(cudaMemcpyAsync(&st, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  std::memcpy(&st, c->h_state, sizeof st);
   CU(cudaGetLastError());
   c->ev_lm = true;
   if (summary) {
