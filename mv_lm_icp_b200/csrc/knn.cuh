@@ -102,38 +102,13 @@ __device__ __forceinline__ void nn_scan_leaf(const FrameDev& fd, int leaf, NNQue
   }
 }
 
-// depth-first search of the subtree rooted at `root` (near child first), pruning with bound32
-template <bool F32>
-__device__ __forceinline__ void nn_dfs(const FrameDev& fd, int root, NNQuery& s) {
-  const int L = fd.n_leaf_pad;
-  int stk_n[20]; float stk_lb[20]; int sp = 0;
-  int node = root;
-  while (true) {
-    if (node >= L) {
-      nn_scan_leaf<F32>(fd, node - L, s);
-    } else {
-      const int c0 = 2 * node;
-      const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
-      const bool first0 = l0 <= l1;
-      const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
-      if (ln <= s.bound32) {
-        if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
-        node = first0 ? c0 : c0 + 1;
-        continue;
-      }
-    }
-    bool found = false;
-    while (sp > 0) {
-      --sp;
-      if (stk_lb[sp] <= s.bound32) { node = stk_n[sp]; found = true; break; }
-    }
-    if (!found) break;
-  }
-}
-
 // Exact 1-NN.  start_leaf >= 0: the leaf holding a good guess (previous round's match); < 0: greedy descent.
 // Equivalent to a full depth-first search whose first root-to-leaf path is given: the start leaf is scanned, then the
 // sibling subtree of every ancestor, bottom-up (nearest first), is searched if its box can still hold a closer point.
+// Control flow is "while-while": an inner loop advances the traversal (box tests only) until the lane owns a leaf to
+// scan or runs out of work; leaves are scanned outside it, so lanes of a warp scan their leaves together instead of
+// interleaving leaf scans with other lanes' node steps.
+constexpr int NN_STACK = 64;   // >= 2 * depth: flagged siblings + far children of one descent
 template <bool F32>
 __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int start_leaf) {
   const int L = fd.n_leaf_pad;
@@ -148,17 +123,36 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
     leaf_node = node;
   } else leaf_node = L + start_leaf;
   nn_scan_leaf<F32>(fd, leaf_node - L, s);
-  // phase 1 (lock-step across the warp, independent loads): which sibling subtrees can matter at all
-  unsigned mask = 0u;
-#pragma unroll 4
-  for (int l = 0; l < fd.depth; ++l)
-    mask |= (box_lb32(fd.boxes, (leaf_node >> l) ^ 1, s) <= s.bound32 ? 1u : 0u) << l;
-  // phase 2: search them bottom-up; the bound only shrinks, so each is re-checked when its turn comes
-  while (mask) {
-    const int l = __ffs(mask) - 1;
-    mask &= mask - 1;
+
+  int stk_n[NN_STACK]; float stk_lb[NN_STACK]; int sp = 0;
+  // sibling subtrees that can matter at all, pushed top-down so that the nearest (lowest) one is popped first
+  for (int l = fd.depth - 1; l >= 0; --l) {
     const int sib = (leaf_node >> l) ^ 1;
-    if (box_lb32(fd.boxes, sib, s) <= s.bound32) nn_dfs<F32>(fd, sib, s);
+    const float lb = box_lb32(fd.boxes, sib, s);
+    if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
+  }
+  while (true) {
+    int pending = -1;
+    int node = -1;
+    while (true) {               // traversal: box tests only
+      if (node < 0) {
+        if (sp == 0) break;
+        --sp;
+        if (stk_lb[sp] > s.bound32) continue;
+        node = stk_n[sp];
+      }
+      if (node >= L) { pending = node - L; break; }
+      const int c0 = 2 * node;
+      const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
+      const bool first0 = l0 <= l1;
+      const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
+      if (ln <= s.bound32) {
+        if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+        node = first0 ? c0 : c0 + 1;
+      } else node = -1;
+    }
+    if (pending < 0) break;      // stack exhausted
+    nn_scan_leaf<F32>(fd, pending, s);
   }
 }
 
