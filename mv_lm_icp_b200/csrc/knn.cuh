@@ -83,31 +83,37 @@ __device__ __forceinline__ float box_lb32(const Box* __restrict__ boxes, int nod
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
+// one candidate that passed the fp32 screen: exact fp64 distance in the reference's operation order
 template <bool F32>
-__device__ __forceinline__ void nn_scan_leaf(const FrameDev& fd, int leaf, NNQuery& s) {
-  const int64_t b = (int64_t)leaf * LEAF;
-  const int cnt = min(LEAF, fd.n - (int)b);
-#pragma unroll 4
-  for (int i = 0; i < cnt; ++i) {
-    const float4 r = __ldg(fd.pts_sf + b + i);
-    const float dx = s.fx - r.x, dy = s.fy - r.y, dz = s.fz - r.z;
-    const float d32 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    if (d32 <= s.bound32) {
-      double px, py, pz; int pi;
-      if (F32) { px = (double)r.x; py = (double)r.y; pz = (double)r.z; pi = __float_as_int(r.w); }
-      else Rec<false>::load(fd.pts_s, b + i, px, py, pz, pi);
-      const double d = d2_rn(s.qx, s.qy, s.qz, px, py, pz);
-      if (d < s.best || (d == s.best && pi < s.bi)) { s.best = d; s.bi = pi; nn_tighten(s); }
-    }
-  }
+__device__ __forceinline__ void nn_exact(const FrameDev& fd, int64_t pos, const float4& r, NNQuery& s) {
+  double px, py, pz; int pi;
+  if (F32) { px = (double)r.x; py = (double)r.y; pz = (double)r.z; pi = __float_as_int(r.w); }
+  else Rec<false>::load(fd.pts_s, pos, px, py, pz, pi);
+  const double d = d2_rn(s.qx, s.qy, s.qz, px, py, pz);
+  if (d < s.best || (d == s.best && pi < s.bi)) { s.best = d; s.bi = pi; nn_tighten(s); }
+}
+
+__device__ __forceinline__ float pt_d32(const float4& r, const NNQuery& s) {
+  const float dx = s.fx - r.x, dy = s.fy - r.y, dz = s.fz - r.z;
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+// two points of a leaf per step (the point arrays are padded with +inf up to a multiple of LEAF)
+template <bool F32>
+__device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int sub, NNQuery& s) {
+  const int64_t pos = (int64_t)leaf * LEAF + 2 * sub;
+  const float4 r0 = __ldg(fd.pts_sf + pos), r1 = __ldg(fd.pts_sf + pos + 1);
+  const float d0 = pt_d32(r0, s), d1 = pt_d32(r1, s);
+  if (d0 <= s.bound32) nn_exact<F32>(fd, pos, r0, s);
+  if (d1 <= s.bound32) nn_exact<F32>(fd, pos + 1, r1, s);
 }
 
 // Exact 1-NN.  start_leaf >= 0: the leaf holding a good guess (previous round's match); < 0: greedy descent.
 // Equivalent to a full depth-first search whose first root-to-leaf path is given: the start leaf is scanned, then the
 // sibling subtree of every ancestor, bottom-up (nearest first), is searched if its box can still hold a closer point.
-// Control flow is "while-while": an inner loop advances the traversal (box tests only) until the lane owns a leaf to
-// scan or runs out of work; leaves are scanned outside it, so lanes of a warp scan their leaves together instead of
-// interleaving leaf scans with other lanes' node steps.
+// The search loop is made of uniform steps -- "test two things": the two child boxes of an internal node, or two
+// points of a leaf (a leaf takes LEAF/2 steps) -- so that the lanes of a warp, which sit at different nodes, still
+// execute the same instructions; only the trip count differs between lanes.
 constexpr int NN_STACK = 64;   // >= 2 * depth: flagged siblings + far children of one descent
 template <bool F32>
 __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int start_leaf) {
@@ -122,7 +128,8 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
     }
     leaf_node = node;
   } else leaf_node = L + start_leaf;
-  nn_scan_leaf<F32>(fd, leaf_node - L, s);
+#pragma unroll
+  for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32>(fd, leaf_node - L, sub, s);
 
   int stk_n[NN_STACK]; float stk_lb[NN_STACK]; int sp = 0;
   // sibling subtrees that can matter at all, pushed top-down so that the nearest (lowest) one is popped first
@@ -131,28 +138,27 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
     const float lb = box_lb32(fd.boxes, sib, s);
     if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
   }
+  int node = -1, sub = 0;
   while (true) {
-    int pending = -1;
-    int node = -1;
-    while (true) {               // traversal: box tests only
-      if (node < 0) {
-        if (sp == 0) break;
-        --sp;
-        if (stk_lb[sp] > s.bound32) continue;
-        node = stk_n[sp];
-      }
-      if (node >= L) { pending = node - L; break; }
+    if (node < 0) {
+      if (sp == 0) break;
+      --sp;
+      if (stk_lb[sp] > s.bound32) continue;
+      node = stk_n[sp]; sub = 0;
+    }
+    if (node >= L) {
+      nn_leaf_step<F32>(fd, node - L, sub, s);
+      if (++sub == LEAF / 2) node = -1;
+    } else {
       const int c0 = 2 * node;
       const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
       const bool first0 = l0 <= l1;
       const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
       if (ln <= s.bound32) {
         if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
-        node = first0 ? c0 : c0 + 1;
+        node = first0 ? c0 : c0 + 1; sub = 0;
       } else node = -1;
     }
-    if (pending < 0) break;      // stack exhausted
-    nn_scan_leaf<F32>(fd, pending, s);
   }
 }
 

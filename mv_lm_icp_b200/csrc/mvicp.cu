@@ -189,6 +189,14 @@ static void pack_records(bool f32, const double* xyz, const int32_t* order, cons
   }
 }
 
+static void pad_records(bool f32, void* recs, int64_t n, int64_t n_pad) {
+  const int32_t w = INT32_MAX;
+  for (int64_t i = n; i < n_pad; ++i) {
+    if (f32) { float4 r; r.x = r.y = r.z = INFINITY; std::memcpy(&r.w, &w, 4); reinterpret_cast<float4*>(recs)[i] = r; }
+    else { double4a r; r.x = r.y = r.z = INFINITY; const long long wl = w; std::memcpy(&r.w, &wl, 8); reinterpret_cast<double4a*>(recs)[i] = r; }
+  }
+}
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -279,13 +287,16 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     const int64_t n = n_pts[f];
     void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr;
     CU(cudaMalloc(&d_o, rec * n)); c->frame_allocs.push_back(d_o);
-    CU(cudaMalloc(&d_s, rec * n)); c->frame_allocs.push_back(d_s);
+    const int64_t n_pad = ((n + LEAF - 1) / LEAF) * LEAF;   // tree-order arrays are padded to whole leaves with +inf points
+    CU(cudaMalloc(&d_s, rec * n_pad)); c->frame_allocs.push_back(d_s);
     CU(cudaMalloc(&d_b, sizeof(Box) * builds[f].boxes.size())); c->frame_allocs.push_back(d_b);
     stage.resize(rec * n);
     pack_records(f32, pts[f], nullptr, nullptr, n, stage.data());
     CU(cudaMemcpy(d_o, stage.data(), rec * n, cudaMemcpyHostToDevice));
+    stage.resize(rec * n_pad);
     pack_records(f32, pts[f], builds[f].order.data(), builds[f].order.data(), n, stage.data());
-    CU(cudaMemcpy(d_s, stage.data(), rec * n, cudaMemcpyHostToDevice));
+    pad_records(f32, stage.data(), n, n_pad);
+    CU(cudaMemcpy(d_s, stage.data(), rec * n_pad, cudaMemcpyHostToDevice));
     if (nor && nor[f]) {
       CU(cudaMalloc(&d_n, rec * n)); c->frame_allocs.push_back(d_n);
       pack_records(f32, nor[f], nullptr, nullptr, n, stage.data());
@@ -294,10 +305,11 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     CU(cudaMemcpy(d_b, builds[f].boxes.data(), sizeof(Box) * builds[f].boxes.size(), cudaMemcpyHostToDevice));
     if (f32) d_sf = d_s;
     else {   // rounded fp32 copy used only to screen candidates; exact arithmetic reads pts_s
-      CU(cudaMalloc(&d_sf, sizeof(float4) * n)); c->frame_allocs.push_back(d_sf);
-      stage.resize(sizeof(float4) * n);
+      CU(cudaMalloc(&d_sf, sizeof(float4) * n_pad)); c->frame_allocs.push_back(d_sf);
+      stage.resize(sizeof(float4) * n_pad);
       pack_records(true, pts[f], builds[f].order.data(), builds[f].order.data(), n, stage.data());
-      CU(cudaMemcpy(d_sf, stage.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+      pad_records(true, stage.data(), n, n_pad);
+      CU(cudaMemcpy(d_sf, stage.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
     }
     CU(cudaMalloc(&d_pos, sizeof(int32_t) * n)); c->frame_allocs.push_back(d_pos);
     CU(cudaMemcpy(d_pos, builds[f].pos_of.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
