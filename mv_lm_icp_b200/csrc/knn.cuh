@@ -118,7 +118,18 @@ constexpr int NN_STACK = 64;   // >= 2 * depth: flagged siblings + far children 
 template <bool F32>
 __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int start_leaf) {
   const int L = fd.n_leaf_pad;
-  int leaf_node;
+  int leaf_node = -1;
+  if (start_leaf >= 0) {
+    leaf_node = L + start_leaf;
+#pragma unroll
+    for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32>(fd, start_leaf, sub, s);
+    // a stale guess (the poses moved a lot since it was made) leaves a loose bound, and everything inside that ball
+    // would be visited on the way up: if the guess is further than a few leaf sizes, descend greedily instead
+    const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
+    const float4 u = __ldg(b), v = __ldg(b + 1);
+    const float ex = u.w - u.x, ey = v.x - u.y, ez = v.y - u.z;
+    if (s.bound32 > 16.0f * fmaf(ez, ez, fmaf(ey, ey, ex * ex))) start_leaf = -1;
+  }
   if (start_leaf < 0) {
     int node = 1;
     while (node < L) {
@@ -126,10 +137,12 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
       const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
       node = (l1 < l0) ? c0 + 1 : c0;
     }
-    leaf_node = node;
-  } else leaf_node = L + start_leaf;
+    if (node != leaf_node) {
 #pragma unroll
-  for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32>(fd, leaf_node - L, sub, s);
+      for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32>(fd, node - L, sub, s);
+    }
+    leaf_node = node;
+  }
 
   int stk_n[NN_STACK]; float stk_lb[NN_STACK]; int sp = 0;
   // sibling subtrees that can matter at all, pushed top-down so that the nearest (lowest) one is popped first
