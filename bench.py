@@ -216,8 +216,6 @@ def run_ours(args, cfg):
     def run_rounds(k, e2e):
         """k rounds from the initial poses; per-round device ms (events on the engine's stream) and stats."""
         eng.set_graph(edges)             # forget the previous trajectory's matches: round 0 is a cold, unseeded search
-        if world > 1:
-            eng.comm_init(uid, rank, world)
         eng.set_poses(sc["poses_init"])
         per = []
         poses = sc["poses_init"]
