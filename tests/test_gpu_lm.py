@@ -128,3 +128,27 @@ def test_nonrigid_pose_is_reported(golden_dir):
     assert ei.value.code == 5
     eng.optimize(PARAM_AA, COST_P2P, True)    # angle-axis has no such issue: any matrix maps to a true rotation
     eng.close()
+
+
+def test_full_size_round_matches_oracle(oracle):
+    """BASELINE config 3 shape (20 views x 200k pts, point-to-plane, SE3, robust): one full outer round on the GPU vs the
+    oracle LM on the GPU's own correspondences (their parity is covered by test_gpu_corr.py::test_full_size_properties)."""
+    M, N = 20, 200_000
+    sc = scene(M, N, 3)
+    edges = synth.ring_edges(M, 2)
+    eng = Engine(); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
+    eng.correspond(0.05)
+    corr, w = [], []
+    for e, (s_, d_) in enumerate(edges):
+        if s_ == 0:
+            corr.append((np.zeros(0, np.int32), np.zeros(0, np.int32))); w.append(np.float32(0)); continue
+        f, sec, dist, ww = eng.get_edge(e)
+        corr.append((f, sec)); w.append(ww)
+    summ = eng.optimize(PARAM_SE3, COST_P2PLANE, True)
+    P = eng.get_poses()
+    Pref, sref, _ = oracle.optimize(sc["pts"], sc["nor"], sc["poses_init"], edges, corr, w, param=PARAM_SE3, cost=COST_P2PLANE,
+                                    robust=True, threads=oracle.max_threads())
+    assert summ["num_iterations"] == sref["num_iterations"] and summ["termination"] == sref["termination"]
+    assert abs(summ["final_cost"] - sref["final_cost"]) <= 1e-9 * sref["final_cost"]
+    assert pose_rel_err(P, Pref) <= TIGHT_TOL
+    eng.close()
