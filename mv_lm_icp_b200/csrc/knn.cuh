@@ -142,6 +142,12 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
   // sibling subtrees that can matter at all, pushed top-down so that the nearest (lowest) one is popped first
   for (int l = fd.depth - 1; l >= 0; --l) {
     const int sib = (leaf_node >> l) ^ 1;
+    // cheap pre-filter (what nanoflann prunes with, nanoflann.hpp:1237-1243): the split plane between the two siblings
+    const float face = __ldg(reinterpret_cast<const float*>(fd.boxes + sib) + 15);
+    const int axis = __float_as_int(face) & 3;
+    const float qa = axis == 0 ? s.fx : (axis == 1 ? s.fy : s.fz);
+    const float dpl = (sib & 1) ? face - qa : qa - face;
+    if (dpl > 0.f && dpl * dpl > s.bound32) continue;
     const float lb = box_lb32(fd.boxes, sib, s);
     if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
   }

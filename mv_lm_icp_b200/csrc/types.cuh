@@ -10,6 +10,7 @@
 // (checked at upload); arithmetic is fp64 either way, so results do not depend on the choice.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace mv {
 
@@ -28,6 +29,7 @@ constexpr int NBLK = 56;         // stride of a block
 // axis-aligned box of a tilted patch is as thick as the patch is wide, an oriented one is as thick as the surface is
 // rough, which is what lets a query far from the surface discard its neighbours' neighbours.
 //   every point p of the node satisfies |a_i . (p - c)| <= e_i (i = 0..2) for the stored fp32 a_i, c (checked in fp64)
+//   pad = one-sided bound of the node's points along its parent's split axis (see tree_build.h), axis in the low 2 bits
 struct Box { float c[3]; float e0; float a0[3]; float e1; float a1[3]; float e2; float a2[3]; float pad; };
 
 struct double4a { double x, y, z, w; };   // 32-byte record for the fp64 storage mode

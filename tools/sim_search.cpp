@@ -1,0 +1,84 @@
+// tools/sim_search.cpp -- CPU model of csrc/knn.cuh's search loop that COUNTS steps (box tests, point tests) per query.
+// Development aid only (lets tree/bound variants be compared without a GPU); not part of the product or the oracle.
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+#include "../mv_lm_icp_b200/csrc/tree_build.h"
+
+struct Sim { HostFrameBuild b; std::vector<float> px, py, pz; std::vector<int> pi; int64_t n; const double* pts; };
+
+static inline float lb32(const Box& b, float fx, float fy, float fz) {
+  const float dx = fx - b.c[0], dy = fy - b.c[1], dz = fz - b.c[2];
+  const float p0 = b.a0[0] * dx + b.a0[1] * dy + b.a0[2] * dz, p1 = b.a1[0] * dx + b.a1[1] * dy + b.a1[2] * dz, p2 = b.a2[0] * dx + b.a2[1] * dy + b.a2[2] * dz;
+  const float g0 = std::fmax(std::fabs(p0) - b.e0, 0.f), g1 = std::fmax(std::fabs(p1) - b.e1, 0.f), g2 = std::fmax(std::fabs(p2) - b.e2, 0.f);
+  return g0 * g0 + g1 * g1 + g2 * g2;
+}
+
+extern "C" {
+void sim_config(int max_leaves, double ratio) { g_tree_pca_max_leaves = max_leaves; g_tree_pca_ratio = ratio; }
+void* sim_build(const double* pts, int64_t n) {
+  Sim* s = new Sim(); s->n = n; s->pts = pts;
+  build_frame(pts, n, s->b);
+  const int64_t npad = ((n + LEAF - 1) / LEAF) * LEAF;
+  s->px.assign(npad, INFINITY); s->py.assign(npad, INFINITY); s->pz.assign(npad, INFINITY); s->pi.assign(npad, INT32_MAX);
+  for (int64_t i = 0; i < n; ++i) { const int o = s->b.order[i]; s->px[i] = (float)pts[3 * o]; s->py[i] = (float)pts[3 * o + 1]; s->pz[i] = (float)pts[3 * o + 2]; s->pi[i] = o; }
+  return s;
+}
+void sim_free(void* h) { delete (Sim*)h; }
+int sim_leaf_of(void* h, int orig) { return ((Sim*)h)->b.pos_of[orig] / LEAF; }
+// returns NN original index; counts[0] = box tests, counts[1] = point tests, counts[2] = loop steps
+int sim_query(void* h, const double* q, int start_leaf, int reseed, int64_t* counts) {
+  Sim& s = *(Sim*)h; const HostFrameBuild& t = s.b; const int L = t.n_leaf_pad;
+  const float fx = (float)q[0], fy = (float)q[1], fz = (float)q[2];
+  float bound = INFINITY; double best = INFINITY; int bi = INT32_MAX;
+  int64_t nb = 0, np = 0, ns = 0;
+  auto scan2 = [&](int leaf, int sub) {
+    for (int j = 0; j < 2; ++j) {
+      const int64_t pos = (int64_t)leaf * LEAF + 2 * sub + j; ++np;
+      const float dx = fx - s.px[pos], dy = fy - s.py[pos], dz = fz - s.pz[pos];
+      const float d32 = dx * dx + dy * dy + dz * dz;
+      if (d32 <= bound) {
+        const double ex = q[0] - (double)s.px[pos], ey = q[1] - (double)s.py[pos], ez = q[2] - (double)s.pz[pos];
+        const double d = ex * ex + ey * ey + ez * ez;
+        if (d < best || (d == best && s.pi[pos] < bi)) { best = d; bi = s.pi[pos]; const double r = std::sqrt(best) + 1e-6; bound = (float)(r * r * 1.000001); }
+      }
+    }
+  };
+  int leaf_node = -1;
+  if (start_leaf >= 0) {
+    leaf_node = L + start_leaf;
+    for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(start_leaf, sub); ++ns; }
+    const Box& b = t.boxes[leaf_node];
+    if (reseed && bound > 64.f * (b.e0 * b.e0 + b.e1 * b.e1 + b.e2 * b.e2)) start_leaf = -1;
+  }
+  if (start_leaf < 0) {
+    int node = 1;
+    while (node < L) { const float l0 = lb32(t.boxes[2 * node], fx, fy, fz), l1 = lb32(t.boxes[2 * node + 1], fx, fy, fz); nb += 2; ++ns; node = (l1 < l0) ? 2 * node + 1 : 2 * node; }
+    if (node != leaf_node) for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(node - L, sub); ++ns; }
+    leaf_node = node;
+  }
+  std::vector<int> sn; std::vector<float> sl;
+  for (int l = t.depth - 1; l >= 0; --l) {
+    const int sib = (leaf_node >> l) ^ 1;
+    const float face = t.boxes[sib].pad; uint32_t bits; std::memcpy(&bits, &face, 4); const int axis = bits & 3;
+    const float qa = axis == 0 ? fx : (axis == 1 ? fy : fz);
+    const float dpl = (sib & 1) ? face - qa : qa - face; ++counts[3];
+    if (dpl > 0.f && dpl * dpl > bound) continue;
+    const float lb = lb32(t.boxes[sib], fx, fy, fz); ++nb; if (lb <= bound) { sn.push_back(sib); sl.push_back(lb); } }
+  ns += t.depth;
+  int node = -1, sub = 0;
+  while (true) {
+    if (node < 0) { if (sn.empty()) break; const int nn = sn.back(); const float ll = sl.back(); sn.pop_back(); sl.pop_back(); if (ll > bound) continue; node = nn; sub = 0; }
+    ++ns;
+    if (node >= L) { scan2(node - L, sub); if (++sub == LEAF / 2) node = -1; }
+    else {
+      const int c0 = 2 * node; const float l0 = lb32(t.boxes[c0], fx, fy, fz), l1 = lb32(t.boxes[c0 + 1], fx, fy, fz); nb += 2;
+      const bool f0 = l0 <= l1; const float ln = f0 ? l0 : l1, lf = f0 ? l1 : l0;
+      if (ln <= bound) { if (lf <= bound) { sn.push_back(f0 ? c0 + 1 : c0); sl.push_back(lf); } node = f0 ? c0 : c0 + 1; sub = 0; } else node = -1;
+    }
+  }
+  counts[0] += nb; counts[1] += np; counts[2] += ns;
+  return bi;
+}
+}
