@@ -9,7 +9,7 @@
 //     point its traversal meets (nanoflann.hpp:1210) -- documented deviation, counted by the tests;
 //   * cutoff           sqrt(d2) < (double)thresh                 frame.cpp:142,156.
 //
-// Search structure: implicit binary tree of oriented boxes over leaves in left-balanced KD order (types.cuh), walked in fp32 with a
+// Search structure: implicit binary AABB tree over leaves in left-balanced KD order (types.cuh), walked in fp32 with a
 // conservative screen and re-ranked in fp64 (see "fp32 screening" below): the answer is the exact fp64 arg-min.
 #pragma once
 #include <cuda_runtime.h>
@@ -44,10 +44,10 @@ __device__ __forceinline__ double d2_rn(double qx, double qy, double qz, double 
 // The tree is walked in fp32.  A candidate (or a box) is looked at exactly only if its fp32 distance does not exceed
 // bound32, an upper bound -- rounded up, with the fp32 error budget added -- of the current exact best:
 //   per-axis error of an fp32 difference (query rounded to fp32, rounded subtraction; stored coordinates exact in the
-//   fp32 storage mode, rounded in the fp64 mode)  <= delta = 2^-23 (|q|_inf + absmax); a projection on a box axis
-//   (three more rounded products/sums) stays below 2.5 delta, and the fp32 axes are orthonormal to ~1e-7
-//   => computed d32 <= (D + 2.5 sqrt(3) delta)^2 (1 + 4e-7) for a point at true distance D, or for the lower bound D
-//   of a box, so every point with D^2 <= best satisfies d32 <= bound32 := ru[(sqrt(best) + ea)^2 (1 + 1e-6)], ea = 6 sqrt(3) delta
+//   fp32 storage mode, rounded in the fp64 mode)  <= delta = 2^-23 (|q|_inf + absmax)
+//   => computed d32 <= (D + sqrt(3) delta)^2 (1 + 2^-24)^3 for a point at true distance D (same for a box lower bound or
+//   a split-plane distance), so every point with D^2 <= best satisfies
+//   d32 <= bound32 := ru[(sqrt(best) + ea)^2 (1 + 1e-6)], ea = 6 sqrt(3) delta
 //   (bound32 itself is evaluated in fp32 with every operation rounded up).
 // Whatever passes the screen is re-evaluated with the reference's fp64 operation sequence (d2_rn) on the exact
 // coordinates, and only that value decides: the result is the exact arg-min with the lowest-index tie rule.
@@ -66,16 +66,13 @@ __device__ __forceinline__ void nn_tighten(NNQuery& s) {
   s.bound32 = __fmul_ru(__fmaf_ru(s.eaf, __fmaf_ru(2.0f, r, s.eaf), b), 1.000001f);
 }
 
-// squared distance from the query to the node's oriented box (0 inside); empty nodes carry e = -inf => +inf
 __device__ __forceinline__ float box_lb32(const Box* __restrict__ boxes, int node, const NNQuery& s) {
   const float4* b = reinterpret_cast<const float4*>(boxes + node);
-  const float4 q0 = __ldg(b), q1 = __ldg(b + 1), q2 = __ldg(b + 2), q3 = __ldg(b + 3);   // (c, e0) (a0, e1) (a1, e2) (a2, -)
-  const float dx = s.fx - q0.x, dy = s.fy - q0.y, dz = s.fz - q0.z;
-  const float p0 = fmaf(q1.z, dz, fmaf(q1.y, dy, q1.x * dx));
-  const float p1 = fmaf(q2.z, dz, fmaf(q2.y, dy, q2.x * dx));
-  const float p2 = fmaf(q3.z, dz, fmaf(q3.y, dy, q3.x * dx));
-  const float g0 = fmaxf(fabsf(p0) - q0.w, 0.f), g1 = fmaxf(fabsf(p1) - q1.w, 0.f), g2 = fmaxf(fabsf(p2) - q2.w, 0.f);
-  return fmaf(g2, g2, fmaf(g1, g1, g0 * g0));
+  const float4 u = __ldg(b), v = __ldg(b + 1);   // u = lo.xyz, hi.x ; v = hi.yz
+  const float dx = fmaxf(fmaxf(u.x - s.fx, s.fx - u.w), 0.f);
+  const float dy = fmaxf(fmaxf(u.y - s.fy, s.fy - v.x), 0.f);
+  const float dz = fmaxf(fmaxf(u.z - s.fz, s.fz - v.y), 0.f);
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
 // one candidate that passed the fp32 screen: exact fp64 distance in the reference's operation order
@@ -121,8 +118,9 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
     // a stale guess (the poses moved a lot since it was made) leaves a loose bound, and everything inside that ball
     // would be visited on the way up: if the guess is further than a few leaf sizes, descend greedily instead
     const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
-    const float ex = __ldg(b).w, ey = __ldg(b + 1).w, ez = __ldg(b + 2).w;     // half extents of the leaf
-    if (s.bound32 > 64.0f * fmaf(ez, ez, fmaf(ey, ey, ex * ex))) start_leaf = -1;
+    const float4 u = __ldg(b), v = __ldg(b + 1);
+    const float ex = u.w - u.x, ey = v.x - u.y, ez = v.y - u.z;                 // extents of the leaf
+    if (s.bound32 > 16.0f * fmaf(ez, ez, fmaf(ey, ey, ex * ex))) start_leaf = -1;
   }
   if (start_leaf < 0) {
     int node = 1;
@@ -143,7 +141,7 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
   for (int l = fd.depth - 1; l >= 0; --l) {
     const int sib = (leaf_node >> l) ^ 1;
     // cheap pre-filter (what nanoflann prunes with, nanoflann.hpp:1237-1243): the split plane between the two siblings
-    const float face = __ldg(reinterpret_cast<const float*>(fd.boxes + sib) + 15);
+    const float face = __ldg(fd.faces + sib);
     const int axis = __float_as_int(face) & 3;
     const float qa = axis == 0 ? s.fx : (axis == 1 ? s.fy : s.fz);
     const float dpl = (sib & 1) ? face - qa : qa - face;

@@ -224,7 +224,7 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
   std::vector<char> stage;
   for (int f = 0; f < M; ++f) {
     const int64_t n = n_pts[f];
-    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr;
+    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr, *d_fc = nullptr;
     CU(cudaMalloc(&d_o, rec * n)); c->frame_allocs.push_back(d_o);
     const int64_t n_pad = ((n + LEAF - 1) / LEAF) * LEAF;   // tree-order arrays are padded to whole leaves with +inf points
     CU(cudaMalloc(&d_s, rec * n_pad)); c->frame_allocs.push_back(d_s);
@@ -250,9 +250,11 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
       pad_records(true, stage.data(), n, n_pad);
       CU(cudaMemcpy(d_sf, stage.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
     }
+    CU(cudaMalloc(&d_fc, sizeof(float) * builds[f].faces.size())); c->frame_allocs.push_back(d_fc);
+    CU(cudaMemcpy(d_fc, builds[f].faces.data(), sizeof(float) * builds[f].faces.size(), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&d_pos, sizeof(int32_t) * n)); c->frame_allocs.push_back(d_pos);
     CU(cudaMemcpy(d_pos, builds[f].pos_of.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
-    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const float4*)d_sf, (const Box*)d_b, (const int32_t*)d_pos, (int32_t)n,
+    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n,
                               builds[f].n_leaf_pad, builds[f].depth, builds[f].absmax};
   }
   RET(c->d_frames.reserve(sizeof(FrameDev) * M));

@@ -4,7 +4,7 @@
 //   pts_o / nor_o : points / normals in the caller's order, one 16-byte (float4) or 32-byte (double4)
 //                   record each -> the LM kernel's coalesced src stream and its dst gathers;
 //   pts_s         : the same points in left-balanced KD order ("tree order"), record.w = original index;
-//   boxes         : implicit binary tree of oriented boxes over leaves of LEAF consecutive tree-order points,
+//   boxes         : implicit binary AABB tree over leaves of LEAF consecutive tree-order points,
 //                   heap order (root = 1, children 2i, 2i+1, leaves at [n_leaf_pad, 2 n_leaf_pad)).
 // float storage is used iff every coordinate of every frame is exactly fp32-representable
 // (checked at upload); arithmetic is fp64 either way, so results do not depend on the choice.
@@ -25,12 +25,7 @@ constexpr int BLK_A = 0, BLK_B = 21, BLK_COST = 27, BLK_SW = 28, BLK_SWP = 29, B
 constexpr int NBLK_PLANE = 28;   // entries used by a point-to-plane-only solve
 constexpr int NBLK = 56;         // stride of a block
 
-// Oriented bounding box of a tree node, 64 B (sibling pairs share a 128-B line).  Scans are thin surface patches: an
-// axis-aligned box of a tilted patch is as thick as the patch is wide, an oriented one is as thick as the surface is
-// rough, which is what lets a query far from the surface discard its neighbours' neighbours.
-//   every point p of the node satisfies |a_i . (p - c)| <= e_i (i = 0..2) for the stored fp32 a_i, c (checked in fp64)
-//   pad = one-sided bound of the node's points along its parent's split axis (see tree_build.h), axis in the low 2 bits
-struct Box { float c[3]; float e0; float a0[3]; float e1; float a1[3]; float e2; float a2[3]; float pad; };
+struct Box { float lo[3]; float hi[3]; float pad[2]; };   // 32 B fp32 AABB; child pairs are 64-B contiguous
 
 struct double4a { double x, y, z, w; };   // 32-byte record for the fp64 storage mode
 
@@ -39,7 +34,8 @@ struct FrameDev {
   const void* nor_o;     // may be null
   const void* pts_s;     // exact coordinates in tree order, .w = original index (int bits / int64 bits)
   const float4* pts_sf;  // fp32 screening copy in tree order, .w = original index; == pts_s in the fp32 storage mode
-  const Box* boxes;      // 2 * n_leaf_pad entries (entry 0 unused), fp32 oriented boxes, extents rounded outward
+  const Box* boxes;      // 2 * n_leaf_pad entries (entry 0 unused), fp32 AABBs rounded outward
+  const float* faces;    // per node: one-sided bound along the parent's split axis, axis in the low 2 mantissa bits
   const int32_t* pos_of; // original index -> position in tree order (seed -> leaf)
   int32_t n;             // points
   int32_t n_leaf_pad;    // power of two >= ceil(n / LEAF)

@@ -9,14 +9,13 @@
 struct Sim { HostFrameBuild b; std::vector<float> px, py, pz; std::vector<int> pi; int64_t n; const double* pts; };
 
 static inline float lb32(const Box& b, float fx, float fy, float fz) {
-  const float dx = fx - b.c[0], dy = fy - b.c[1], dz = fz - b.c[2];
-  const float p0 = b.a0[0] * dx + b.a0[1] * dy + b.a0[2] * dz, p1 = b.a1[0] * dx + b.a1[1] * dy + b.a1[2] * dz, p2 = b.a2[0] * dx + b.a2[1] * dy + b.a2[2] * dz;
-  const float g0 = std::fmax(std::fabs(p0) - b.e0, 0.f), g1 = std::fmax(std::fabs(p1) - b.e1, 0.f), g2 = std::fmax(std::fabs(p2) - b.e2, 0.f);
-  return g0 * g0 + g1 * g1 + g2 * g2;
+  const float dx = std::fmax(std::fmax(b.lo[0] - fx, fx - b.hi[0]), 0.f), dy = std::fmax(std::fmax(b.lo[1] - fy, fy - b.hi[1]), 0.f),
+              dz = std::fmax(std::fmax(b.lo[2] - fz, fz - b.hi[2]), 0.f);
+  return dx * dx + dy * dy + dz * dz;
 }
 
 extern "C" {
-void sim_config(int max_leaves, double ratio) { g_tree_pca_max_leaves = max_leaves; g_tree_pca_ratio = ratio; }
+void sim_config(int, double) {}
 void* sim_build(const double* pts, int64_t n) {
   Sim* s = new Sim(); s->n = n; s->pts = pts;
   build_frame(pts, n, s->b);
@@ -50,7 +49,8 @@ int sim_query(void* h, const double* q, int start_leaf, int reseed, int64_t* cou
     leaf_node = L + start_leaf;
     for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(start_leaf, sub); ++ns; }
     const Box& b = t.boxes[leaf_node];
-    if (reseed && bound > 64.f * (b.e0 * b.e0 + b.e1 * b.e1 + b.e2 * b.e2)) start_leaf = -1;
+    const float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+    if (reseed && bound > 16.f * (ex * ex + ey * ey + ez * ez)) start_leaf = -1;
   }
   if (start_leaf < 0) {
     int node = 1;
@@ -61,7 +61,7 @@ int sim_query(void* h, const double* q, int start_leaf, int reseed, int64_t* cou
   std::vector<int> sn; std::vector<float> sl;
   for (int l = t.depth - 1; l >= 0; --l) {
     const int sib = (leaf_node >> l) ^ 1;
-    const float face = t.boxes[sib].pad; uint32_t bits; std::memcpy(&bits, &face, 4); const int axis = bits & 3;
+    const float face = t.faces[sib]; uint32_t bits; std::memcpy(&bits, &face, 4); const int axis = bits & 3;
     const float qa = axis == 0 ? fx : (axis == 1 ? fy : fz);
     const float dpl = (sib & 1) ? face - qa : qa - face; ++counts[3];
     if (dpl > 0.f && dpl * dpl > bound) continue;
