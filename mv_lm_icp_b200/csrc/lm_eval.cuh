@@ -190,16 +190,137 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
   }
 }
 
-// blocks[e][NBLK] = sum of the edge's tile partials in tile order (deterministic); zero for edges not owned.
-__global__ void lm_reduce_kernel(const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
-                                 double* __restrict__ blocks, int nused, const int* __restrict__ done_flag) {
+// One CTA per edge: (1) sum the edge's tile partials in tile order (deterministic), (2) expand the block into the edge's
+// 12x12 pair matrix and 12-vector over the two frames' parameterisation tangents:
+//   canonical pair matrix (over [xi_s, xi_k]):
+//     point-to-plane part  [I | -Q]^T A [I | -Q],  Q = Ad(T_rel^-1) = [[R^T, -R^T [t]x], [0, R^T]]  (R = R_rel, t = t_rel)
+//     point-to-point part  from the moments, world-frame rows J_s = R_s [I | -[p]x], J_k = -R_k [I | -[q]x]
+//   then Hp = Kpair^T Hcan Kpair with Kpair = diag(K_s, K_k) (tangent_map), gp = Kpair^T [b ; -Q^T b].
+// out[e] = Hp (144) | gp (12) | cost | pad; zeros for edges this rank does not own (an all-reduce then gathers).
+constexpr int EDGE_THREADS = 64;
+constexpr int EOUT_ = 160;
+__global__ void __launch_bounds__(EDGE_THREADS)
+lm_edge_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
+               int nused, const Rt* __restrict__ frame_Rt, const double* __restrict__ K_eval, double* __restrict__ out,
+               const int* __restrict__ done_flag) {
   if (*done_flag) return;
-  const int e = blockIdx.x, j = threadIdx.x;
-  if (j >= NBLK) return;
-  if (j >= nused) { blocks[(size_t)e * NBLK + j] = 0.0; return; }
-  double v = 0.0;
-  for (int t = edge_tile_begin[e]; t < edge_tile_begin[e + 1]; ++t) v += partial[(size_t)t * NBLK + j];
-  blocks[(size_t)e * NBLK + j] = v;
+  const int e = blockIdx.x, tid = threadIdx.x;
+  __shared__ double blk[NBLK], Q[36], AQ[36], Hcan[144], T1[144], Rt_[9];
+  double* o = out + (size_t)EOUT_ * e;
+  if (!edges[e].owned) { for (int i = tid; i < EOUT_; i += EDGE_THREADS) o[i] = 0.0; return; }
+  if (tid < NBLK) {
+    double v = 0.0;
+    if (tid < nused) for (int t = edge_tile_begin[e]; t < edge_tile_begin[e + 1]; ++t) v += partial[(size_t)t * NBLK + tid];
+    blk[tid] = v;
+  }
+  if (tid == 0) {
+    const Rt a = frame_Rt[edges[e].src], k = frame_Rt[edges[e].dst];
+    double R[9]; matTmul(k.R, a.R, R);
+    const double dt[3] = {a.t[0] - k.t[0], a.t[1] - k.t[1], a.t[2] - k.t[2]};
+    double t[3]; matTvec(k.R, dt, t);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt_[3 * i + j] = R[3 * j + i];
+    const double tx[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+    double RtTx[9]; matmul(Rt_, tx, RtTx);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        Q[6 * i + j] = Rt_[3 * i + j]; Q[6 * i + 3 + j] = -RtTx[3 * i + j];
+        Q[6 * (3 + i) + j] = 0.0;      Q[6 * (3 + i) + 3 + j] = Rt_[3 * i + j];
+      }
+  }
+  for (int i = tid; i < 144; i += EDGE_THREADS) Hcan[i] = 0.0;
+  __syncthreads();
+  if (tid == 0 && blk[BLK_SW] != 0.0) {   // point-to-point part of the canonical pair matrix
+    const double* m = blk;
+    const double sw = m[BLK_SW];
+    const double* sp = m + BLK_SWP; const double* sq = m + BLK_SWQ;
+    const double pp[9] = {m[BLK_SWPP], m[BLK_SWPP + 1], m[BLK_SWPP + 2], m[BLK_SWPP + 1], m[BLK_SWPP + 3], m[BLK_SWPP + 4],
+                          m[BLK_SWPP + 2], m[BLK_SWPP + 4], m[BLK_SWPP + 5]};
+    const double qq[9] = {m[BLK_SWQQ], m[BLK_SWQQ + 1], m[BLK_SWQQ + 2], m[BLK_SWQQ + 1], m[BLK_SWQQ + 3], m[BLK_SWQQ + 4],
+                          m[BLK_SWQQ + 2], m[BLK_SWQQ + 4], m[BLK_SWQQ + 5]};
+    const double* pq = m + BLK_SWPQ;
+    const double px[9] = {0, -sp[2], sp[1], sp[2], 0, -sp[0], -sp[1], sp[0], 0};   // [sum w p]x
+    const double qx[9] = {0, -sq[2], sq[1], sq[2], 0, -sq[0], -sq[1], sq[0], 0};
+    const double trp = pp[0] + pp[4] + pp[8], trq = qq[0] + qq[4] + qq[8];
+    double RtQx[9]; matmul(Rt_, qx, RtQx);      // R^T [swq]x
+    double PxRt[9]; matmul(px, Rt_, PxRt);      // [swp]x R^T
+    double* Hc_ = Hcan;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const double dij = (i == j) ? 1.0 : 0.0;
+        // (s,s) and (k,k): [[w I, -[wp]x], [[wp]x, tr(wpp) I - wpp]]
+        Hc_[12 * i + j] = sw * dij;                         Hc_[12 * (6 + i) + 6 + j] = sw * dij;
+        Hc_[12 * i + 3 + j] = -px[3 * i + j];               Hc_[12 * (6 + i) + 9 + j] = -qx[3 * i + j];
+        Hc_[12 * (3 + i) + j] = px[3 * i + j];              Hc_[12 * (9 + i) + 6 + j] = qx[3 * i + j];
+        Hc_[12 * (3 + i) + 3 + j] = trp * dij - pp[3 * i + j];
+        Hc_[12 * (9 + i) + 9 + j] = trq * dij - qq[3 * i + j];
+        // (s,k) = -[I | -[p]x]^T R^T [I | -[q]x]
+        double ww = 0.0;   // sum_{c,d} wpq[c][d] (E_c R^T E_d)_{ij},  (E_c)_{ik} = eps(i,c,k)
+        for (int c2 = 0; c2 < 3; ++c2)
+          for (int d2 = 0; d2 < 3; ++d2) {
+            double acc = 0.0;
+            for (int kk = 0; kk < 3; ++kk)
+              for (int ll = 0; ll < 3; ++ll) {
+                const int e1 = (i - c2) * (c2 - kk) * (kk - i), e2 = (ll - d2) * (d2 - j) * (j - ll);
+                if (e1 && e2) acc += 0.25 * (double)(e1 * e2) * Rt_[3 * kk + ll];
+              }
+            ww += pq[3 * c2 + d2] * acc;
+          }
+        const double sk_uu = -sw * Rt_[3 * i + j], sk_uw = RtQx[3 * i + j], sk_wu = -PxRt[3 * i + j], sk_ww = ww;
+        Hc_[12 * i + 6 + j] = sk_uu;        Hc_[12 * (6 + j) + i] = sk_uu;
+        Hc_[12 * i + 9 + j] = sk_uw;        Hc_[12 * (9 + j) + i] = sk_uw;
+        Hc_[12 * (3 + i) + 6 + j] = sk_wu;  Hc_[12 * (6 + j) + 3 + i] = sk_wu;
+        Hc_[12 * (3 + i) + 9 + j] = sk_ww;  Hc_[12 * (9 + j) + 3 + i] = sk_ww;
+      }
+  }
+  if (tid < 36) {      // AQ = A Q
+    const int i = tid / 6, j = tid - 6 * i;
+    double s = 0;
+    for (int m = 0; m < 6; ++m) {
+      const int a = min(i, m), b = max(i, m);
+      s += blk[BLK_A + a * 6 - (a * (a - 1)) / 2 + (b - a)] * Q[6 * m + j];
+    }
+    AQ[tid] = s;
+  }
+  __syncthreads();
+  for (int r = tid; r < 144; r += EDGE_THREADS) {     // Hcan += [I | -Q]^T A [I | -Q]
+    const int a = r / 12, b = r - 12 * a;
+    double v;
+    if (a < 6 && b < 6) { const int lo = min(a, b), hi = max(a, b); v = blk[BLK_A + lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)]; }
+    else if (a < 6) v = -AQ[6 * a + (b - 6)];
+    else if (b < 6) v = -AQ[6 * b + (a - 6)];
+    else { v = 0; for (int i = 0; i < 6; ++i) v += Q[6 * i + (a - 6)] * AQ[6 * i + (b - 6)]; }
+    Hcan[r] += v;
+  }
+  __syncthreads();
+  const double* Ks = K_eval + 36 * edges[e].src; const double* Kk = K_eval + 36 * edges[e].dst;
+  for (int r = tid; r < 144; r += EDGE_THREADS) {     // T1 = Hcan Kpair
+    const int a = r / 12, b = r - 12 * a;
+    const double* Kb = b < 6 ? Ks : Kk; const int off = b < 6 ? 0 : 6;
+    double v = 0; for (int m = 0; m < 6; ++m) v += Hcan[12 * a + off + m] * Kb[6 * m + (b - off)];
+    T1[r] = v;
+  }
+  __syncthreads();
+  for (int r = tid; r < 157; r += EDGE_THREADS) {     // Hp = Kpair^T T1 (144), gp = Kpair^T [b ; -Q^T b] (12), cost
+    if (r < 144) {
+      const int a = r / 12, b = r - 12 * a;
+      const double* Ka = a < 6 ? Ks : Kk; const int off = a < 6 ? 0 : 6;
+      double v = 0; for (int m = 0; m < 6; ++m) v += Ka[6 * m + (a - off)] * T1[12 * (off + m) + b];
+      o[r] = v;
+    } else if (r < 156) {
+      const int a = r - 144;
+      const double* bv = blk + BLK_B;
+      const double* Ka = a < 6 ? Ks : Kk; const int off = a < 6 ? 0 : 6;
+      double v = 0;
+      for (int m = 0; m < 6; ++m) {
+        double gm;
+        if (a < 6) gm = bv[m];
+        else { gm = 0; for (int i = 0; i < 6; ++i) gm -= Q[6 * i + m] * bv[i]; }
+        v += Ka[6 * m + (a - off)] * gm;
+      }
+      o[r] = v;
+    } else o[r] = blk[BLK_COST];
+  }
+  if (tid < 3) o[157 + tid] = 0.0;
 }
 
 }  // namespace mv

@@ -17,6 +17,7 @@
 namespace mv {
 
 constexpr int STEP_THREADS = 512;
+constexpr int EOUT = 160;   // doubles per edge produced by lm_edge_kernel: Hp 144 | gp 12 | cost | pad
 
 struct LmState {
   mvicp_lm_options opt;
@@ -28,7 +29,9 @@ struct LmState {
 struct LmWork {
   LmState* S;
   const EdgeDev* edges;
-  const double* blocks;      // [E][NBLK] at the evaluation point (summed over ranks)
+  const double* eout;        // [E][EOUT]: pair matrix (144), pair gradient (12), cost at the evaluation point (summed over ranks)
+  volatile int32_t* host_flag; // mapped pinned ring: (sequence << 1) | done, written at the end of every step
+  int32_t seq;
   double* x;                 // [M][7] accepted point (all frames)
   double* cand;              // [M][7] evaluation point / next candidate
   Rt* Rt_eval;               // [M]
@@ -38,7 +41,7 @@ struct LmWork {
   const int32_t* hb_ptr; const int32_t* hb_row; const int32_t* hb_col; const int32_t* hc_edge; const int32_t* hc_sub; int32_t n_hblocks;
   const int32_t* gb_ptr; const int32_t* gc_edge; const int32_t* gc_side;   // per frame
   const int32_t* rlast; const int32_t* rfirst;   // envelope of the normal matrix: last row touching column j / first column of row r
-  double *H, *g, *Hc, *gc, *scale, *diag, *Lg, *rhs, *step, *Qs, *AQ, *Hcan, *T1, *Hp, *gp;
+  double *H, *g, *Hc, *gc, *scale, *diag, *Lg, *rhs, *step;
   double* poses16;
   int32_t l_in_smem;
 };
@@ -137,136 +140,14 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   __shared__ double red[40];
   __shared__ int s_flag;
   LmState* S = w.S;
-  if (S->done) return;
+  if (S->done) { if (threadIdx.x == 0) { w.host_flag[w.seq & 7] = (w.seq << 1) | 1; __threadfence_system(); } return; }
   const int tid = threadIdx.x, T = blockDim.x;
   const int n = S->n, M = S->M, E = S->E, param = S->param;
   // dynamic shared memory: [colj (n+1) | dg (n+1) | L (n+1) x (n|1) when it fits]
   double* colj = smem; double* dg = smem + (S->n + 1);
   double* L = w.l_in_smem ? smem + 2 * (S->n + 1) : w.Lg;
 
-  // ================= 1. assemble Hc, gc, cost at the evaluation point ===============================
-  // Canonical pair matrix per edge (12x12 over [xi_s, xi_k]):
-  //   point-to-plane part  [I | -Q]^T A [I | -Q],  Q = Ad(T_rel^-1) = [[R^T, -R^T [t]x], [0, R^T]]  (R = R_rel, t = t_rel)
-  //   point-to-point part  from the moments, world-frame rows J_s = R_s [I | -[p]x], J_k = -R_k [I | -[q]x]
-  // then Hp = Kpair^T Hcan Kpair with Kpair = diag(K_s, K_k) (tangent_map), gp = Kpair^T [b ; -Q^T b].
-  for (int e = tid; e < E; e += T) {
-    const Rt a = w.Rt_eval[w.edges[e].src], k = w.Rt_eval[w.edges[e].dst];
-    double R[9]; matTmul(k.R, a.R, R);
-    const double dt[3] = {a.t[0] - k.t[0], a.t[1] - k.t[1], a.t[2] - k.t[2]};
-    double t[3]; matTvec(k.R, dt, t);
-    const double tx[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
-    double Rt_[9]; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt_[3 * i + j] = R[3 * j + i];
-    double RtTx[9]; matmul(Rt_, tx, RtTx);
-    double* Q = w.Qs + 36 * e;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        Q[6 * i + j] = Rt_[3 * i + j]; Q[6 * i + 3 + j] = -RtTx[3 * i + j];
-        Q[6 * (3 + i) + j] = 0.0;      Q[6 * (3 + i) + 3 + j] = Rt_[3 * i + j];
-      }
-    // point-to-point part of the canonical pair matrix
-    const double* m = w.blocks + (size_t)NBLK * e;
-    double* Hc_ = w.Hcan + 144 * e;
-    for (int i = 0; i < 144; ++i) Hc_[i] = 0.0;
-    const double sw = m[BLK_SW];
-    if (sw != 0.0) {
-      const double* sp = m + BLK_SWP; const double* sq = m + BLK_SWQ;
-      const double pp[9] = {m[BLK_SWPP], m[BLK_SWPP + 1], m[BLK_SWPP + 2], m[BLK_SWPP + 1], m[BLK_SWPP + 3], m[BLK_SWPP + 4],
-                            m[BLK_SWPP + 2], m[BLK_SWPP + 4], m[BLK_SWPP + 5]};
-      const double qq[9] = {m[BLK_SWQQ], m[BLK_SWQQ + 1], m[BLK_SWQQ + 2], m[BLK_SWQQ + 1], m[BLK_SWQQ + 3], m[BLK_SWQQ + 4],
-                            m[BLK_SWQQ + 2], m[BLK_SWQQ + 4], m[BLK_SWQQ + 5]};
-      const double* pq = m + BLK_SWPQ;
-      const double px[9] = {0, -sp[2], sp[1], sp[2], 0, -sp[0], -sp[1], sp[0], 0};   // [sum w p]x
-      const double qx[9] = {0, -sq[2], sq[1], sq[2], 0, -sq[0], -sq[1], sq[0], 0};
-      const double trp = pp[0] + pp[4] + pp[8], trq = qq[0] + qq[4] + qq[8];
-      double RtQx[9]; matmul(Rt_, qx, RtQx);      // R^T [swq]x
-      double PxRt[9]; matmul(px, Rt_, PxRt);      // [swp]x R^T
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          const double dij = (i == j) ? 1.0 : 0.0;
-          // (s,s) and (k,k): [[w I, -[wp]x], [[wp]x, tr(wpp) I - wpp]]
-          Hc_[12 * i + j] = sw * dij;                         Hc_[12 * (6 + i) + 6 + j] = sw * dij;
-          Hc_[12 * i + 3 + j] = -px[3 * i + j];               Hc_[12 * (6 + i) + 9 + j] = -qx[3 * i + j];
-          Hc_[12 * (3 + i) + j] = px[3 * i + j];              Hc_[12 * (9 + i) + 6 + j] = qx[3 * i + j];
-          Hc_[12 * (3 + i) + 3 + j] = trp * dij - pp[3 * i + j];
-          Hc_[12 * (9 + i) + 9 + j] = trq * dij - qq[3 * i + j];
-          // (s,k) = -[I | -[p]x]^T R^T [I | -[q]x]
-          double ww = 0.0;   // sum_{c,d} wpq[c][d] (E_c R^T E_d)_{ij},  (E_c)_{ik} = eps(i,c,k)
-          for (int c2 = 0; c2 < 3; ++c2)
-            for (int d2 = 0; d2 < 3; ++d2) {
-              double acc = 0.0;
-              for (int kk = 0; kk < 3; ++kk)
-                for (int ll = 0; ll < 3; ++ll) {
-                  const int e1 = (i - c2) * (c2 - kk) * (kk - i), e2 = (ll - d2) * (d2 - j) * (j - ll);
-                  if (e1 && e2) acc += 0.25 * (double)(e1 * e2) * Rt_[3 * kk + ll];
-                }
-              ww += pq[3 * c2 + d2] * acc;
-            }
-          const double sk_uu = -sw * Rt_[3 * i + j], sk_uw = RtQx[3 * i + j], sk_wu = -PxRt[3 * i + j], sk_ww = ww;
-          Hc_[12 * i + 6 + j] = sk_uu;        Hc_[12 * (6 + j) + i] = sk_uu;
-          Hc_[12 * i + 9 + j] = sk_uw;        Hc_[12 * (9 + j) + i] = sk_uw;
-          Hc_[12 * (3 + i) + 6 + j] = sk_wu;  Hc_[12 * (6 + j) + 3 + i] = sk_wu;
-          Hc_[12 * (3 + i) + 9 + j] = sk_ww;  Hc_[12 * (9 + j) + 3 + i] = sk_ww;
-        }
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < E * 36; idx += T) {      // AQ = A Q
-    const int e = idx / 36, r = idx - 36 * e, i = r / 6, j = r - 6 * i;
-    const double* blk = w.blocks + (size_t)NBLK * e;
-    const double* Q = w.Qs + 36 * e;
-    double s = 0;
-    for (int m = 0; m < 6; ++m) {
-      const int a = min(i, m), b = max(i, m);
-      s += blk[BLK_A + a * 6 - (a * (a - 1)) / 2 + (b - a)] * Q[6 * m + j];
-    }
-    w.AQ[idx] = s;
-  }
-  __syncthreads();
-  for (int idx = tid; idx < E * 144; idx += T) {     // Hcan += [I | -Q]^T A [I | -Q]
-    const int e = idx / 144, r = idx - 144 * e, a = r / 12, b = r - 12 * a;
-    const double* blk = w.blocks + (size_t)NBLK * e;
-    const double* Q = w.Qs + 36 * e; const double* AQ = w.AQ + 36 * e;
-    double v;
-    if (a < 6 && b < 6) { const int lo = min(a, b), hi = max(a, b); v = blk[BLK_A + lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)]; }
-    else if (a < 6) v = -AQ[6 * a + (b - 6)];
-    else if (b < 6) v = -AQ[6 * b + (a - 6)];
-    else { v = 0; for (int i = 0; i < 6; ++i) v += Q[6 * i + (a - 6)] * AQ[6 * i + (b - 6)]; }
-    w.Hcan[idx] += v;
-  }
-  __syncthreads();
-  for (int idx = tid; idx < E * 144; idx += T) {     // T1 = Hcan Kpair
-    const int e = idx / 144, r = idx - 144 * e, a = r / 12, b = r - 12 * a;
-    const double* Kb = w.K_eval + 36 * (b < 6 ? w.edges[e].src : w.edges[e].dst);
-    const int off = b < 6 ? 0 : 6;
-    double v = 0; for (int m = 0; m < 6; ++m) v += w.Hcan[144 * e + 12 * a + off + m] * Kb[6 * m + (b - off)];
-    w.T1[idx] = v;
-  }
-  __syncthreads();
-  for (int idx = tid; idx < E * 156; idx += T) {     // Hp = Kpair^T T1 (144), gp = Kpair^T [b ; -Q^T b] (12)
-    const int e = idx / 156, r = idx - 156 * e;
-    if (r < 144) {
-      const int a = r / 12, b = r - 12 * a;
-      const double* Ka = w.K_eval + 36 * (a < 6 ? w.edges[e].src : w.edges[e].dst);
-      const int off = a < 6 ? 0 : 6;
-      double v = 0; for (int m = 0; m < 6; ++m) v += Ka[6 * m + (a - off)] * w.T1[144 * e + 12 * (off + m) + b];
-      w.Hp[144 * e + r] = v;
-    } else {
-      const int a = r - 144;
-      const double* bv = w.blocks + (size_t)NBLK * e + BLK_B;
-      const double* Q = w.Qs + 36 * e;
-      const double* Ka = w.K_eval + 36 * (a < 6 ? w.edges[e].src : w.edges[e].dst);
-      const int off = a < 6 ? 0 : 6;
-      double v = 0;
-      for (int m = 0; m < 6; ++m) {
-        double gm;
-        if (a < 6) gm = bv[m];
-        else { gm = 0; for (int i = 0; i < 6; ++i) gm -= Q[6 * i + m] * bv[i]; }
-        v += Ka[6 * m + (a - off)] * gm;
-      }
-      w.gp[12 * e + a] = v;
-    }
-  }
-  __syncthreads();
+  // ================= 1. gather the per-edge pair matrices (lm_edge_kernel) into Hc, gc; total cost ===================
   for (int idx = tid; idx < n * n; idx += T) w.Hc[idx] = 0.0;
   __syncthreads();
   for (int idx = tid; idx < w.n_hblocks * 36; idx += T) {   // gather into the dense matrix, fixed order
@@ -274,7 +155,7 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     double s = 0;
     for (int c = w.hb_ptr[b]; c < w.hb_ptr[b + 1]; ++c) {
       const int e = w.hc_edge[c], sub = w.hc_sub[c];   // sub: 0 ss, 1 sk, 2 ks, 3 kk
-      s += w.Hp[144 * e + (6 * (sub >> 1) + i) * 12 + 6 * (sub & 1) + j];
+      s += w.eout[(size_t)EOUT * e + (6 * (sub >> 1) + i) * 12 + 6 * (sub & 1) + j];
     }
     w.Hc[(size_t)(w.hb_row[b] + i) * n + w.hb_col[b] + j] = s;
   }
@@ -282,12 +163,12 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     const int f = idx / 6, i = idx - 6 * f;
     if (w.col[f] < 0) continue;
     double s = 0;
-    for (int c = w.gb_ptr[f]; c < w.gb_ptr[f + 1]; ++c) s += w.gp[12 * w.gc_edge[c] + 6 * w.gc_side[c] + i];
+    for (int c = w.gb_ptr[f]; c < w.gb_ptr[f + 1]; ++c) s += w.eout[(size_t)EOUT * w.gc_edge[c] + 144 + 6 * w.gc_side[c] + i];
     w.gc[w.col[f] + i] = s;
   }
   __syncthreads();
   double eval_cost = 0.0;
-  if (tid == 0) { for (int e = 0; e < E; ++e) eval_cost += w.blocks[(size_t)NBLK * e + BLK_COST]; red[33] = eval_cost; }
+  if (tid == 0) { for (int e = 0; e < E; ++e) eval_cost += w.eout[(size_t)EOUT * e + 156]; red[33] = eval_cost; }
   __syncthreads();
   eval_cost = red[33];
 
@@ -443,6 +324,8 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
       pose_of_param(param, xf, w.poses16 + 16 * f);
     }
   }
+  __syncthreads();
+  if (tid == 0) { w.host_flag[w.seq & 7] = (w.seq << 1) | (S->done ? 1 : 0); __threadfence_system(); }
 }
 
 }  // namespace mv

@@ -83,12 +83,11 @@ struct mvicp_ctx {
   std::vector<float> h_weight; std::vector<unsigned long long> h_count;
   // LM
   DevBuf d_state, d_x, d_cand, d_Rt, d_K, d_col, d_H, d_g, d_Hc, d_gc, d_scale, d_diag, d_L, d_rhs, d_step,
-      d_Qs, d_AQ, d_Hcan, d_T1, d_Hp, d_gp, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst;
+      d_eout, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst;
   int n_free = 0, n_hblocks = 0;
   std::vector<int32_t> h_col;
-  int32_t* h_done = nullptr;   // pinned ring of termination flags
   void* h_state = nullptr;     // pinned staging of LmState
-  std::vector<cudaEvent_t> iter_ev;
+  volatile int32_t* h_flag = nullptr; volatile int32_t* d_flag = nullptr;   // mapped pinned ring written by lm_step_kernel
   std::vector<uint8_t> lm_key; uint32_t graph_gen = 0;
   // stats
   mvicp_stats stats{};
@@ -165,8 +164,9 @@ int mvicp_create(const mvicp_config* cfg, mvicp_ctx** out) {
   if (cfg && cfg->stream) c->stream = (cudaStream_t)cfg->stream;
   else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
-  CU(cudaMallocHost((void**)&c->h_done, sizeof(int32_t) * 256));
   CU(cudaMallocHost(&c->h_state, sizeof(LmState)));
+  CU(cudaHostAlloc((void**)&c->h_flag, sizeof(int32_t) * 8, cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer((void**)&c->d_flag, (void*)c->h_flag, 0));
   *out = c;
   return MVICP_OK;
 }
@@ -180,15 +180,15 @@ void mvicp_destroy(mvicp_ctx* c) {
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
                     &c->d_weight, &c->d_median, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
                     &c->d_blocks, &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
-                    &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_Qs, &c->d_AQ, &c->d_Hcan, &c->d_T1, &c->d_Hp, &c->d_gp,
+                    &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
                     &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
-  if (c->h_done) cudaFreeHost(c->h_done);
   if (c->h_state) cudaFreeHost(c->h_state);
-  for (auto& ev : c->iter_ev) cudaEventDestroy(ev);
+  if (c->h_flag) cudaFreeHost((void*)c->h_flag);
+
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -514,9 +514,7 @@ static int prepare_lm(mvicp_ctx* c, int n) {
   RET(c->d_L.reserve(sizeof(double) * (size_t)(n + 1) * (n | 1)));
   RET(c->d_g.reserve(sizeof(double) * n)); RET(c->d_gc.reserve(sizeof(double) * n)); RET(c->d_scale.reserve(sizeof(double) * n));
   RET(c->d_diag.reserve(sizeof(double) * n)); RET(c->d_rhs.reserve(sizeof(double) * n)); RET(c->d_step.reserve(sizeof(double) * n));
-  RET(c->d_Qs.reserve(sizeof(double) * 36 * E)); RET(c->d_AQ.reserve(sizeof(double) * 36 * E));
-  RET(c->d_Hcan.reserve(sizeof(double) * 144 * E)); RET(c->d_T1.reserve(sizeof(double) * 144 * E));
-  RET(c->d_Hp.reserve(sizeof(double) * 144 * E)); RET(c->d_gp.reserve(sizeof(double) * 12 * E));
+  RET(c->d_eout.reserve(sizeof(double) * EOUT * E));
   return MVICP_OK;
 }
 
@@ -611,7 +609,8 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   CU(cudaMemcpyAsync(c->d_state.p, c->h_state, sizeof st, cudaMemcpyHostToDevice, c->stream));
 
   LmWork w{};
-  w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.blocks = c->d_blocks.as<double>();
+  w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.eout = c->d_eout.as<double>();
+  w.host_flag = c->d_flag;
   w.x = c->d_x.as<double>(); w.cand = c->d_cand.as<double>(); w.Rt_eval = c->d_Rt.as<Rt>(); w.K_eval = c->d_K.as<double>();
   w.col = c->d_col.as<int32_t>();
   w.hb_ptr = c->d_hb_ptr.as<int32_t>(); w.hb_row = c->d_hb_row.as<int32_t>(); w.hb_col = c->d_hb_col.as<int32_t>();
@@ -620,9 +619,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   w.gb_ptr = c->d_gb_ptr.as<int32_t>(); w.gc_edge = c->d_gc_edge.as<int32_t>(); w.gc_side = c->d_gc_side.as<int32_t>();
   w.H = c->d_H.as<double>(); w.g = c->d_g.as<double>(); w.Hc = c->d_Hc.as<double>(); w.gc = c->d_gc.as<double>();
   w.scale = c->d_scale.as<double>(); w.diag = c->d_diag.as<double>(); w.Lg = c->d_L.as<double>(); w.rhs = c->d_rhs.as<double>();
-  w.step = c->d_step.as<double>(); w.Qs = c->d_Qs.as<double>(); w.AQ = c->d_AQ.as<double>(); w.Hcan = c->d_Hcan.as<double>();
-  w.T1 = c->d_T1.as<double>(); w.Hp = c->d_Hp.as<double>();
-  w.gp = c->d_gp.as<double>(); w.poses16 = c->d_poses.as<double>();
+  w.step = c->d_step.as<double>(); w.poses16 = c->d_poses.as<double>();
   const size_t l_bytes = sizeof(double) * (size_t)(n + 1) * (n | 1);
   const size_t vec_bytes = sizeof(double) * 2 * (size_t)(n + 1);
   w.l_in_smem = (l_bytes + vec_bytes) <= 220 * 1024 ? 1 : 0;
@@ -635,8 +632,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   // The loop is pipelined one iteration deep: iteration i+1 is enqueued before the host learns whether iteration i
   // terminated, so the GPU never waits for the host; kernels of an iteration issued after termination exit at once.
   const int max_evals = opt.max_num_iterations + 2;
-  const int ring = 8;   // at most two iterations are in flight
-  while ((int)c->iter_ev.size() < ring) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->iter_ev.push_back(e); }
+  for (int i = 0; i < 8; ++i) c->h_flag[i] = 0;
   c->eval_ev_used = 0;
   int issued = 0, seen = 0;
   const int* done_flag = &w.S->done;
@@ -646,22 +642,32 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     if (c->f32) launch_eval<true>(c, cost, st.robust, done_flag); else launch_eval<false>(c, cost, st.robust, done_flag);
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used + 1], c->stream));
     c->eval_ev_used += 2;
-    lm_reduce_kernel<<<E, 64, 0, c->stream>>>(c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(), c->d_blocks.as<double>(),
-                                             cost == COST_P2PLANE ? NBLK_PLANE : NBLK, done_flag);
+    lm_edge_kernel<<<E, EDGE_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(),
+                                                      cost == COST_P2PLANE ? NBLK_PLANE : NBLK, c->d_Rt.as<Rt>(), c->d_K.as<double>(),
+                                                      c->d_eout.as<double>(), done_flag);
     if (c->comm && c->world > 1)
-      NC(ncclAllReduce(c->d_blocks.p, c->d_blocks.p, (size_t)NBLK * E, ncclDouble, ncclSum, c->comm, c->stream));
+      NC(ncclAllReduce(c->d_eout.p, c->d_eout.p, (size_t)EOUT * E, ncclDouble, ncclSum, c->comm, c->stream));
+    w.seq = issued + 1;
     lm_step_kernel<<<1, STEP_THREADS, dyn, c->stream>>>(w);
     c->stats.kernel_launches += (c->n_eval_tiles ? 1 : 0) + 2;
-    CU(cudaMemcpyAsync(c->h_done + (issued % ring), done_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaEventRecord(c->iter_ev[issued % ring], c->stream));
     ++issued;
     return MVICP_OK;
   };
   RET(issue());
   while (true) {
     if (issued - seen < 2 && issued <= max_evals) RET(issue());
-    CU(cudaEventSynchronize(c->iter_ev[seen % ring]));
-    const bool fin = c->h_done[seen % ring] != 0;
+    // the step kernel publishes (sequence << 1 | done) into mapped pinned memory: spin on it, no stream round trip
+    const int want = seen + 1;
+    int32_t v;
+    long spins = 0;
+    while (((v = c->h_flag[want & 7]) >> 1) != want) {
+      if ((++spins & 0xfffff) == 0 && cudaStreamQuery(c->stream) != cudaErrorNotReady) {   // kernels died or stream drained
+        v = c->h_flag[want & 7];
+        if ((v >> 1) != want) { CU(cudaGetLastError()); return fail(MVICP_ERR_CUDA, "LM step %d never reported", want); }
+        break;
+      }
+    }
+    const bool fin = (v & 1) != 0;
     ++seen;
     if (fin || seen > max_evals) break;
   }
