@@ -62,10 +62,28 @@ def build(force=False):
 _lib = None
 
 
+def _preload_nccl():
+    """libmvicp.so needs libnccl.so.2.  PyTorch bundles a newer NCCL than the system one under the same soname; whichever
+    is loaded first wins for the whole process, and torch fails to import on top of the older one.  Load torch's copy
+    first when it exists (no torch import needed), so that both libraries share it regardless of import order."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            p = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                C.CDLL(p, mode=C.RTLD_GLOBAL)
+                return p
+    except Exception:
+        pass
+    return None
+
+
 def lib():
     global _lib
     if _lib is None:
         build()
+        _preload_nccl()
         _lib = C.CDLL(LIB_PATH)
         _lib.mvicp_last_error.restype = C.c_char_p
     return _lib
