@@ -100,20 +100,17 @@ __device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int s
   if (d1 <= s.bound32) nn_exact<F32>(fd, pos + 1, r1, s);
 }
 
-// ---- the search, in two parts -----------------------------------------------------------------------------------
-// Equivalent to a full depth-first search whose first root-to-leaf path is given (by the previous round's match, or
-// by a greedy descent): (1) nn_begin scans that start leaf and marks, bottom-up, the sibling subtree of every ancestor
-// whose box can still hold a closer point (split-plane pre-filter, then box test) -> `mask` (bit l = level l above the
-// leaf); (2) nn_drain searches the marked subtrees nearest first, re-checking each against the shrinking bound.
-// Part 1 has the same shape for every query; part 2 is a loop of uniform steps -- "test two things": the two child
-// boxes of a node, or two points of a leaf (a leaf takes LEAF/2 steps) -- whose trip count varies wildly between
-// queries, which is why knn_kernel runs it from a shared pool with lanes re-filling themselves (see there).
-constexpr int NN_STACK = 40;   // far children pending on one descent: <= depth
-
+// Exact 1-NN.  start_leaf >= 0: the leaf holding a good guess (previous round's match); < 0: greedy descent.
+// Equivalent to a full depth-first search whose first root-to-leaf path is given: the start leaf is scanned, then the
+// sibling subtree of every ancestor, bottom-up (nearest first), is searched if its box can still hold a closer point.
+// The search loop is made of uniform steps -- "test two things": the two child boxes of an internal node, or two
+// points of a leaf (a leaf takes LEAF/2 steps) -- so that the lanes of a warp, which sit at different nodes, still
+// execute the same instructions; only the trip count differs between lanes.
+constexpr int NN_STACK = 64;   // >= 2 * depth: flagged siblings + far children of one descent
 template <bool F32>
-__device__ __forceinline__ void nn_begin(const FrameDev& fd, NNQuery& s, int start_leaf, int& leaf_node, unsigned& mask) {
+__device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int start_leaf) {
   const int L = fd.n_leaf_pad;
-  leaf_node = -1;
+  int leaf_node = -1;
   if (start_leaf >= 0) {
     leaf_node = L + start_leaf;
 #pragma unroll
@@ -138,8 +135,10 @@ __device__ __forceinline__ void nn_begin(const FrameDev& fd, NNQuery& s, int sta
     }
     leaf_node = node;
   }
-  mask = 0u;
-  for (int l = 0; l < fd.depth; ++l) {
+
+  int stk_n[NN_STACK]; float stk_lb[NN_STACK]; int sp = 0;
+  // sibling subtrees that can matter at all, pushed top-down so that the nearest (lowest) one is popped first
+  for (int l = fd.depth - 1; l >= 0; --l) {
     const int sib = (leaf_node >> l) ^ 1;
     // cheap pre-filter (what nanoflann prunes with, nanoflann.hpp:1237-1243): the split plane between the two siblings
     const float face = __ldg(fd.faces + sib);
@@ -147,52 +146,31 @@ __device__ __forceinline__ void nn_begin(const FrameDev& fd, NNQuery& s, int sta
     const float qa = axis == 0 ? s.fx : (axis == 1 ? s.fy : s.fz);
     const float dpl = (sib & 1) ? face - qa : qa - face;
     if (dpl > 0.f && dpl * dpl > s.bound32) continue;
-    if (box_lb32(fd.boxes, sib, s) <= s.bound32) mask |= 1u << l;
+    const float lb = box_lb32(fd.boxes, sib, s);
+    if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
   }
-}
-
-// per-lane traversal state of part 2
-struct NNWalk { int leaf_node; unsigned mask; int node, sub, sp; };
-
-// one uniform step; returns false when the query is finished
-template <bool F32>
-__device__ __forceinline__ bool nn_step(const FrameDev& fd, NNQuery& s, NNWalk& w, int* stk_n, float* stk_lb) {
-  const int L = fd.n_leaf_pad;
-  if (w.node < 0) {
-    if (w.sp > 0) {
-      --w.sp;
-      if (stk_lb[w.sp] > s.bound32) return true;
-      w.node = stk_n[w.sp]; w.sub = 0;
-    } else if (w.mask) {
-      const int l = __ffs(w.mask) - 1;
-      w.mask &= w.mask - 1;
-      const int sib = (w.leaf_node >> l) ^ 1;
-      if (box_lb32(fd.boxes, sib, s) > s.bound32) return true;
-      w.node = sib; w.sub = 0;
-    } else return false;
+  int node = -1, sub = 0;
+  while (true) {
+    if (node < 0) {
+      if (sp == 0) break;
+      --sp;
+      if (stk_lb[sp] > s.bound32) continue;
+      node = stk_n[sp]; sub = 0;
+    }
+    if (node >= L) {
+      nn_leaf_step<F32>(fd, node - L, sub, s);
+      if (++sub == LEAF / 2) node = -1;
+    } else {
+      const int c0 = 2 * node;
+      const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
+      const bool first0 = l0 <= l1;
+      const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
+      if (ln <= s.bound32) {
+        if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+        node = first0 ? c0 : c0 + 1; sub = 0;
+      } else node = -1;
+    }
   }
-  if (w.node >= L) {
-    nn_leaf_step<F32>(fd, w.node - L, w.sub, s);
-    if (++w.sub == LEAF / 2) w.node = -1;
-  } else {
-    const int c0 = 2 * w.node;
-    const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
-    const bool first0 = l0 <= l1;
-    const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
-    if (ln <= s.bound32) {
-      if (lf <= s.bound32) { stk_n[w.sp] = first0 ? c0 + 1 : c0; stk_lb[w.sp] = lf; ++w.sp; }
-      w.node = first0 ? c0 : c0 + 1; w.sub = 0;
-    } else w.node = -1;
-  }
-  return true;
-}
-
-template <bool F32>
-__device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int start_leaf) {
-  NNWalk w; w.node = -1; w.sub = 0; w.sp = 0;
-  nn_begin<F32>(fd, s, start_leaf, w.leaf_node, w.mask);
-  int stk_n[NN_STACK]; float stk_lb[NN_STACK];
-  while (nn_step<F32>(fd, s, w, stk_n, stk_lb)) {}
 }
 
 __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, double qz, float absmax) {
@@ -204,51 +182,29 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
   s.bound32 = __int_as_float(0x7f800000);
 }
 
-// All (edge, src point) queries of a tile (KNN_TILE consecutive src points of one edge, in the src frame's tree order so
-// that neighbouring threads ask about neighbouring points).
-//   Phase 1 -- every thread, KNN_QPT queries in turn: the reference's query transform (fp64, no FMA contraction), the
-//     previous round's match as the start leaf, nn_begin.  A query with nothing marked is finished; the others are
-//     parked in a shared-memory pool (48 B each: query, best so far, start leaf, marks).
-//   Phase 2 -- lanes take parked queries from the pool one at a time and run the step loop to the end, re-filling
-//     themselves when they finish: the step count per query has a heavy tail (a query near a centre of curvature of the
-//     dst surface sees hundreds of equidistant candidates), and without re-filling a warp waits for its slowest lane.
-struct NNParked { double qx, qy, qz, best; int bi, orig, leaf_node; unsigned mask; };
-
+// One thread per (edge, src point) query; src points are walked in the src frame's tree order so that the
+// lanes of a warp descend the dst tree together.
 template <bool F32>
-__device__ __forceinline__ void knn_store(int32_t* __restrict__ corr, double* __restrict__ d2out, int64_t slot, double best, int bi,
-                                          double thresh) {
-  const bool inlier = __dsqrt_rn(best) < thresh;     // sqrt(pointDistSquared) < thresh, frame.cpp:142,156
-  corr[slot] = inlier ? bi : ~bi;
-  d2out[slot] = best;
-}
-
-template <bool F32>
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_TILE)
 knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
            const Tile* __restrict__ tiles, int32_t* __restrict__ corr, double* __restrict__ d2out,
            const int32_t* __restrict__ seed, double thresh) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ EdgeXf sx;
-  __shared__ NNParked pool[KNN_TILE];
-  __shared__ int pool_n, pool_next;
   {
     const double* g = reinterpret_cast<const double*>(xfs + t.edge);
     double* s = reinterpret_cast<double*>(&sx);
     for (int i = threadIdx.x; i < (int)(sizeof(EdgeXf) / sizeof(double)); i += blockDim.x) s[i] = g[i];
-    if (threadIdx.x == 0) { pool_n = 0; pool_next = 0; }
   }
   __syncthreads();
   const FrameDev fs = frames[e.src];
   const FrameDev fd = frames[e.dst];
-  // ---- phase 1
-#pragma unroll 1
-  for (int r = 0; r < KNN_QPT; ++r) {
-    const int ks = t.start + r * KNN_THREADS + threadIdx.x;
-    if (ks >= e.n_src) continue;
+  const int ks = t.start + threadIdx.x;
+  if (ks < e.n_src) {
     double px, py, pz; int orig;
     Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
-    // g = R_s p + t_s ; q = Rinv_d (g - t_d)
+    // g = R_s p + t_s
     const double gx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[0], px), __dmul_rn(sx.Rs[1], py)), __dmul_rn(sx.Rs[2], pz)), sx.ts[0]);
     const double gy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[3], px), __dmul_rn(sx.Rs[4], py)), __dmul_rn(sx.Rs[5], pz)), sx.ts[1]);
     const double gz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[6], px), __dmul_rn(sx.Rs[7], py)), __dmul_rn(sx.Rs[8], pz)), sx.ts[2]);
@@ -256,6 +212,7 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
     const double qx = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[0], ex), __dmul_rn(sx.Rinv[1], ey)), __dmul_rn(sx.Rinv[2], ez));
     const double qy = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[3], ex), __dmul_rn(sx.Rinv[4], ey)), __dmul_rn(sx.Rinv[5], ez));
     const double qz = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[6], ex), __dmul_rn(sx.Rinv[7], ey)), __dmul_rn(sx.Rinv[8], ez));
+
     NNQuery nq; nn_query_init(nq, qx, qy, qz, fd.absmax);
     int start_leaf = -1;
     if (seed) {   // previous round's match: a valid first guess, the search stays exact
@@ -263,35 +220,11 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
       const int si = sd >= 0 ? sd : ~sd;
       if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
     }
-    int leaf_node; unsigned mask;
-    nn_begin<F32>(fd, nq, start_leaf, leaf_node, mask);
-    if (mask == 0u) knn_store<F32>(corr, d2out, e.off + orig, nq.best, nq.bi, thresh);
-    else {
-      const int slot = atomicAdd(&pool_n, 1);
-      NNParked p; p.qx = qx; p.qy = qy; p.qz = qz; p.best = nq.best; p.bi = nq.bi; p.orig = orig; p.leaf_node = leaf_node; p.mask = mask;
-      pool[slot] = p;
-    }
-  }
-  __syncthreads();
-  // ---- phase 2
-  const int n_parked = pool_n;
-  int stk_n[NN_STACK]; float stk_lb[NN_STACK];
-  NNQuery nq; NNWalk w; int orig = -1;
-  bool busy = false;
-  while (true) {
-    if (!busy) {
-      const int slot = atomicAdd(&pool_next, 1);
-      if (slot >= n_parked) break;
-      const NNParked p = pool[slot];
-      nn_query_init(nq, p.qx, p.qy, p.qz, fd.absmax);
-      nq.best = p.best; nq.bi = p.bi; nn_tighten(nq);
-      w.leaf_node = p.leaf_node; w.mask = p.mask; w.node = -1; w.sub = 0; w.sp = 0;
-      orig = p.orig; busy = true;
-    }
-    if (!nn_step<F32>(fd, nq, w, stk_n, stk_lb)) {
-      knn_store<F32>(corr, d2out, e.off + orig, nq.best, nq.bi, thresh);
-      busy = false;
-    }
+    nn_search<F32>(fd, nq, start_leaf);
+    const double best = nq.best; const int bi = nq.bi;
+    const bool inlier = __dsqrt_rn(best) < thresh;
+    corr[e.off + orig] = inlier ? bi : ~bi;
+    d2out[e.off + orig] = best;
   }
 }
 

@@ -386,7 +386,7 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
   if (c->n_knn_tiles)
-    knn_kernel<F32><<<c->n_knn_tiles, KNN_THREADS, 0, c->stream>>>(
+    knn_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
         c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
         c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh);
   CU(cudaEventRecord(c->ev[1], c->stream));

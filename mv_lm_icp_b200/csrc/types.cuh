@@ -15,9 +15,7 @@
 namespace mv {
 
 constexpr int LEAF = 8;          // points per BVH leaf
-constexpr int KNN_THREADS = 256;  // threads per CTA of the NN kernel
-constexpr int KNN_QPT = 3;        // queries per thread (pool of parked queries: 48 B each, static shared memory)
-constexpr int KNN_TILE = KNN_THREADS * KNN_QPT;   // queries per CTA
+constexpr int KNN_TILE = 256;    // queries per CTA of the NN kernel
 constexpr int EVAL_TILE = 2048;  // correspondence slots per CTA of the LM streaming kernel
 constexpr int EVAL_THREADS = 256;
 // per-edge block (doubles):  A = upper 6x6 of the point-to-plane normal matrix in the src frame's canonical tangent,
