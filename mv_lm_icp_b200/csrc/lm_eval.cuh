@@ -323,4 +323,127 @@ lm_edge_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ ed
   if (tid < 3) o[157 + tid] = 0.0;
 }
 
+
+// ---- general path: non-unit quaternions (non-rigid input poses) -------------------------------------------------------
+// Same contract as lm_eval_kernel, for the frame model of frame_general(): y = F v + t with F no rotation, Jacobian rows
+// through the per-frame matrices D_j, c_j (the relative-pose shortcut needs orthogonal F).  The 12x12 pair matrix is
+// accumulated directly, one block per launch to bound the register count (PASS 0: (s,s) + gradient + cost, 1: (s,k),
+// 2: (k,k)); three passes over the correspondences -- this path only runs on inputs that are not rigid transforms.
+constexpr int GBLK = 96;   // stride of a general partial: 78 (upper 12x12) | 12 | 1
+__device__ __forceinline__ int u12(int i, int j) { return i * 12 - (i * (i - 1)) / 2 + (j - i); }
+
+template <bool F32, int COST, int PASS>
+__global__ void __launch_bounds__(EVAL_THREADS)
+lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
+                       int tile_len, const int32_t* __restrict__ corr, const FrameGen* __restrict__ frame_gen,
+                       const float* __restrict__ weight, int robust, double* __restrict__ partial, const int* __restrict__ done_flag) {
+  if (*done_flag) return;
+  const Tile t = tiles[blockIdx.x];
+  const EdgeDev e = edges[t.edge];
+  __shared__ FrameGen gs, gk;
+  __shared__ double sred[EVAL_THREADS / 32][49];
+  {
+    const double* a = reinterpret_cast<const double*>(frame_gen + e.src); const double* b = reinterpret_cast<const double*>(frame_gen + e.dst);
+    double* sa = reinterpret_cast<double*>(&gs); double* sb = reinterpret_cast<double*>(&gk);
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameGen) / sizeof(double)); i += blockDim.x) { sa[i] = a[i]; sb[i] = b[i]; }
+  }
+  __syncthreads();
+  const double a_w = (double)weight[t.edge];
+  const double bb = a_w * a_w, cc = 1.0 / bb;
+  const FrameDev fs = frames[e.src];
+  const FrameDev fd = frames[e.dst];
+  constexpr int NACC = PASS == 0 ? 21 + 12 + 1 : (PASS == 1 ? 36 : 21);
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  const int end = min(t.start + tile_len, e.n_src);
+  for (int k = t.start + threadIdx.x; k < end; k += EVAL_THREADS) {
+    const int c = __ldg(corr + e.off + k);
+    if (c < 0) continue;
+    double p[3], q[3], n[3] = {0, 0, 0}; int dummy;
+    Rec<F32>::load(fs.pts_o, k, p[0], p[1], p[2], dummy);
+    Rec<F32>::load(fd.pts_o, c, q[0], q[1], q[2], dummy);
+    if (COST != COST_P2P) Rec<F32>::load(fd.nor_o, c, n[0], n[1], n[2], dummy);
+    double ys[3], yk[3], n2[3], d[3];
+    matvec(gs.F, p, ys); matvec(gk.F, q, yk); matvec(gk.F, n, n2);
+    for (int i = 0; i < 3; ++i) d[i] = (ys[i] + gs.t[i]) - (yk[i] + gk.t[i]);
+    // columns of the world-frame point Jacobians: dys[j] = D^s_j p + c^s_j, dyk[j] = D^k_j q + c^k_j, dn[j] = D^k_j n
+    for (int blk = 0; blk < 2; ++blk) {
+      const bool plane = blk == 1;
+      if (plane && COST == COST_P2P) continue;
+      if (!plane && COST == COST_P2PLANE) continue;
+      const int nr = plane ? 1 : 3;
+      double J[3][12], r[3];
+      for (int j = 0; j < 6; ++j) {
+        double a3[3], b3[3], c3[3];
+        matvec(gs.D[j], p, a3); matvec(gk.D[j], q, b3);
+        for (int i = 0; i < 3; ++i) { a3[i] += gs.c[j][i]; b3[i] += gk.c[j][i]; }
+        if (plane) {
+          matvec(gk.D[j], n, c3);
+          J[0][j] = n2[0] * a3[0] + n2[1] * a3[1] + n2[2] * a3[2];
+          J[0][6 + j] = -(n2[0] * b3[0] + n2[1] * b3[1] + n2[2] * b3[2]) + (d[0] * c3[0] + d[1] * c3[1] + d[2] * c3[2]);
+        } else {
+          for (int i = 0; i < 3; ++i) { J[i][j] = a3[i]; J[i][6 + j] = -b3[i]; }
+        }
+      }
+      if (plane) r[0] = d[0] * n2[0] + d[1] * n2[1] + d[2] * n2[2]; else { r[0] = d[0]; r[1] = d[1]; r[2] = d[2]; }
+      double s = 0; for (int i = 0; i < nr; ++i) s += r[i] * r[i];
+      double w = 1.0, cst;
+      if (robust) { const double arg = 1.0 + s * cc; w = rsqrt(arg); cst = bb * (arg * w - 1.0); } else cst = 0.5 * s;
+      for (int i = 0; i < nr; ++i) {
+        if (PASS == 0) {
+          int idx = 0;
+          for (int a = 0; a < 6; ++a) { const double wa = w * J[i][a]; for (int b = a; b < 6; ++b) acc[idx++] += wa * J[i][b]; }
+          for (int a = 0; a < 12; ++a) acc[21 + a] += w * J[i][a] * r[i];
+        } else if (PASS == 1) {
+          for (int a = 0; a < 6; ++a) { const double wa = w * J[i][a]; for (int b = 0; b < 6; ++b) acc[6 * a + b] += wa * J[i][6 + b]; }
+        } else {
+          int idx = 0;
+          for (int a = 0; a < 6; ++a) { const double wa = w * J[i][6 + a]; for (int b = a; b < 6; ++b) acc[idx++] += wa * J[i][6 + b]; }
+        }
+      }
+      if (PASS == 0) acc[33] += cst;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = 0; i < NACC; ++i) { const double v = warp_sum(acc[i]); if (lane == 0) sred[wid][i] = v; }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double v = 0.0;
+    for (int w = 0; w < EVAL_THREADS / 32; ++w) v += sred[w][threadIdx.x];
+    // scatter into the 12x12 upper-triangle layout
+    const int i = threadIdx.x; int dst;
+    if (PASS == 0) {
+      if (i < 21) { int a = 0, rem = i; while (rem >= 6 - a) { rem -= 6 - a; ++a; } dst = u12(a, a + rem); }
+      else if (i < 33) dst = 78 + (i - 21);
+      else dst = 90;
+    } else if (PASS == 1) dst = u12(i / 6, 6 + i % 6);
+    else { int a = 0, rem = i; while (rem >= 6 - a) { rem -= 6 - a; ++a; } dst = u12(6 + a, 6 + a + rem); }
+    partial[(size_t)blockIdx.x * GBLK + dst] = v;
+  }
+}
+
+// general-path counterpart of lm_edge_kernel: the partials already are the pair matrix in the parameterisation tangent
+__global__ void __launch_bounds__(EDGE_THREADS)
+lm_edge_general_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
+                       double* __restrict__ out, const int* __restrict__ done_flag) {
+  if (*done_flag) return;
+  const int e = blockIdx.x, tid = threadIdx.x;
+  __shared__ double blk[GBLK];
+  double* o = out + (size_t)EOUT_ * e;
+  if (!edges[e].owned) { for (int i = tid; i < EOUT_; i += EDGE_THREADS) o[i] = 0.0; return; }
+  for (int j = tid; j < 91; j += EDGE_THREADS) {
+    double v = 0.0;
+    for (int t = edge_tile_begin[e]; t < edge_tile_begin[e + 1]; ++t) v += partial[(size_t)t * GBLK + j];
+    blk[j] = v;
+  }
+  __syncthreads();
+  for (int r = tid; r < 160; r += EDGE_THREADS) {
+    if (r < 144) { const int a = r / 12, b = r - 12 * a; o[r] = blk[u12(min(a, b), max(a, b))]; }
+    else if (r < 156) o[r] = blk[78 + (r - 144)];
+    else if (r == 156) o[r] = blk[90];
+    else o[r] = 0.0;
+  }
+}
+
 }  // namespace mv

@@ -36,6 +36,7 @@ struct LmWork {
   double* cand;              // [M][7] evaluation point / next candidate
   Rt* Rt_eval;               // [M]
   double* K_eval;            // [M][36]
+  FrameGen* G_eval;          // [M] general frame model (null unless a quaternion is not unit)
   const int32_t* col;        // [M] first local column or -1
   // block-sparse gather lists (host-built, deterministic order)
   const int32_t* hb_ptr; const int32_t* hb_row; const int32_t* hb_col; const int32_t* hc_edge; const int32_t* hc_sub; int32_t n_hblocks;
@@ -85,6 +86,7 @@ __global__ void lm_init_kernel(LmWork w) {
   for (int i = 0; i < 7; ++i) { w.x[7 * f + i] = x[i]; w.cand[7 * f + i] = x[i]; }
   w.Rt_eval[f] = a;
   for (int i = 0; i < 36; ++i) w.K_eval[36 * f + i] = K[i];
+  if (w.G_eval && S->param != PARAM_AA) frame_general(S->param, x, &w.G_eval[f]);
 }
 
 // ---- dense Cholesky solve --------------------------------------------------------------------------------------
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
       w.Rt_eval[f] = a;
       double K[36]; tangent_map(param, xp, &a, K);
       for (int i = 0; i < 36; ++i) w.K_eval[36 * f + i] = K[i];
+      if (w.G_eval && param != PARAM_AA) frame_general(param, xp, &w.G_eval[f]);
     }
     sn = block_sum(sn, red);
     if (tid == 0) S->step_norm = sqrt(sn);

@@ -80,10 +80,11 @@ struct mvicp_ctx {
   int n_knn_tiles = 0, n_eval_tiles = 0, eval_tile_len = EVAL_TILE;
   int64_t total_slots = 0;
   bool have_corr = false;      // corr[] holds a previous round (usable as seeds)
+  bool nonrigid = false;       // some uploaded pose does not yield a unit quaternion (general LM path for QUAT / SE3)
   std::vector<float> h_weight; std::vector<unsigned long long> h_count;
   // LM
   DevBuf d_state, d_x, d_cand, d_Rt, d_K, d_col, d_H, d_g, d_Hc, d_gc, d_scale, d_diag, d_L, d_rhs, d_step,
-      d_eout, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst;
+      d_eout, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst, d_gen;
   int n_free = 0, n_hblocks = 0;
   std::vector<int32_t> h_col;
   void* h_state = nullptr;     // pinned staging of LmState
@@ -182,7 +183,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_blocks, &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -275,6 +276,16 @@ int mvicp_set_poses(mvicp_ctx* c, const double* poses16, const uint8_t* fixed) {
   CU(cudaMemcpyAsync(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * c->M, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (fixed) c->fixed.assign(fixed, fixed + c->M);
+  // Non-rigid "isometries" (e.g. the reference's Bunny_RealData sample poses) give non-unit quaternions, on which the
+  // reference's quaternion / SE3 functors keep running (no normalisation, so3.hpp:666-668): remember it, the LM step
+  // then uses the general frame model.  Sticky until the next upload: a fixed frame keeps its non-unit quaternion.
+  c->nonrigid = false;
+  for (int f = 0; f < c->M; ++f) {
+    Rt a; pose16_to_Rt(poses16 + 16 * f, &a);
+    double q[4]; quat_of_matrix(a.R, q);
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (!(std::fabs(n2 - 1.0) <= 1e-9)) c->nonrigid = true;
+  }
   return MVICP_OK;
 }
 
@@ -530,6 +541,18 @@ template <bool F32> static void launch_eval(mvicp_ctx* c, int cost, int robust, 
 #undef MV_EVAL
 }
 
+template <bool F32> static void launch_eval_general(mvicp_ctx* c, int cost, int robust, const int* done_flag) {
+  const int nt = c->n_eval_tiles;
+  if (!nt) return;
+#define MV_EVALG(COSTK, PASSK)                                                                                   \
+  lm_eval_general_kernel<F32, COSTK, PASSK><<<nt, EVAL_THREADS, 0, c->stream>>>(                                 \
+      c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
+      c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag)
+#define MV_EVALG3(COSTK) { MV_EVALG(COSTK, 0); MV_EVALG(COSTK, 1); MV_EVALG(COSTK, 2); }
+  if (cost == COST_P2P) MV_EVALG3(COST_P2P) else if (cost == COST_P2PLANE) MV_EVALG3(COST_P2PLANE) else MV_EVALG3(COST_MIXED)
+#undef MV_EVALG3
+#undef MV_EVALG
+}
 extern "C" {
 int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, const mvicp_lm_options* opt_in, mvicp_lm_summary* summary) {
   if (!c || !c->M || !c->E) return fail(MVICP_ERR_STATE, "mvicp_optimize: frames and graph must be set first");
@@ -611,6 +634,9 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   LmWork w{};
   w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.eout = c->d_eout.as<double>();
   w.host_flag = c->d_flag;
+  const bool general = c->nonrigid && param != PARAM_AA;
+  if (general) { RET(c->d_gen.reserve(sizeof(FrameGen) * M)); RET(c->d_partial.reserve(sizeof(double) * GBLK * std::max<size_t>(1, c->n_eval_tiles))); }
+  w.G_eval = general ? c->d_gen.as<FrameGen>() : nullptr;
   w.x = c->d_x.as<double>(); w.cand = c->d_cand.as<double>(); w.Rt_eval = c->d_Rt.as<Rt>(); w.K_eval = c->d_K.as<double>();
   w.col = c->d_col.as<int32_t>();
   w.hb_ptr = c->d_hb_ptr.as<int32_t>(); w.hb_row = c->d_hb_row.as<int32_t>(); w.hb_col = c->d_hb_col.as<int32_t>();
@@ -639,12 +665,17 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   auto issue = [&]() -> int {
     if ((int)c->eval_ev.size() < c->eval_ev_used + 2) { cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); c->eval_ev.push_back(a); c->eval_ev.push_back(b); }
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used], c->stream));
-    if (c->f32) launch_eval<true>(c, cost, st.robust, done_flag); else launch_eval<false>(c, cost, st.robust, done_flag);
+    if (general) { if (c->f32) launch_eval_general<true>(c, cost, st.robust, done_flag); else launch_eval_general<false>(c, cost, st.robust, done_flag); }
+    else if (c->f32) launch_eval<true>(c, cost, st.robust, done_flag); else launch_eval<false>(c, cost, st.robust, done_flag);
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used + 1], c->stream));
     c->eval_ev_used += 2;
-    lm_edge_kernel<<<E, EDGE_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(),
-                                                      cost == COST_P2PLANE ? NBLK_PLANE : NBLK, c->d_Rt.as<Rt>(), c->d_K.as<double>(),
-                                                      c->d_eout.as<double>(), done_flag);
+    if (general)
+      lm_edge_general_kernel<<<E, EDGE_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_edge_tile_begin.as<int32_t>(),
+                                                                c->d_partial.as<double>(), c->d_eout.as<double>(), done_flag);
+    else
+      lm_edge_kernel<<<E, EDGE_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(),
+                                                        cost == COST_P2PLANE ? NBLK_PLANE : NBLK, c->d_Rt.as<Rt>(), c->d_K.as<double>(),
+                                                        c->d_eout.as<double>(), done_flag);
     if (c->comm && c->world > 1)
       NC(ncclAllReduce(c->d_eout.p, c->d_eout.p, (size_t)EOUT * E, ncclDouble, ncclSum, c->comm, c->stream));
     w.seq = issued + 1;
@@ -700,9 +731,8 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     summary->num_evaluations = st.n_evals; summary->num_linear_solves = st.n_solves; summary->reserved = 0;
     summary->initial_cost = st.initial_cost; summary->final_cost = st.x_cost;
   }
-  if (st.nonrigid)
-    return fail(MVICP_ERR_NONRIGID, "a pose's quaternion is not unit (non-rigid Isometry): the unit-quaternion LM path was run; "
-                                    "results differ from the reference's non-unit-quaternion arithmetic");
+  if (st.nonrigid && !general)   // cannot happen after mvicp_set_poses; guards poses that reached the device another way
+    return fail(MVICP_ERR_NONRIGID, "a pose's quaternion is not unit (non-rigid Isometry) but the unit-quaternion LM path was run");
   if (!st.done) return fail(MVICP_ERR_STATE, "LM loop did not terminate within %d evaluations", max_evals);
   return MVICP_OK;
 }

@@ -262,4 +262,58 @@ MV_HD void tangent_map(int param, const double* x, const Rt* a, double* K) {
   }
 }
 
+
+// ---- general (non-unit quaternion) frame model ---------------------------------------------------------------------
+// With a non-unit quaternion (a non-rigid Isometry squeezed through Quaterniond(Matrix3d), icp-ceres.cpp:236 /
+// so3.hpp:666-668) the reference's functors still apply the polynomial map F(q) v = v + 2w(u x v) + 2u x (u x v)
+// (Eigen _transformVector; toRotationMatrix() is the same polynomial), which is linear in v but no rotation, and Ceres
+// differentiates it as such.  For one frame: y(v) = F v + t and, per local tangent direction j of the active
+// parameterisation,  d y(v) / d delta_j = D_j v + c_j,  d (F n) / d delta_j = D_j n,  with
+//   D_j = sum_c P_q[c][j] dF/dq_c,   c_j = P_t[:, j],   P = d Plus(x, delta) / d delta at 0  (7x6, quaternion rows xyzw).
+struct FrameGen { double F[9]; double t[3]; double D[6][9]; double c[6][3]; };
+
+MV_HD void frame_general(int param, const double* x, FrameGen* o) {
+  const double qx = x[0], qy = x[1], qz = x[2], qw = x[3];
+  matrix_of_quat(x, o->F);
+  o->t[0] = x[4]; o->t[1] = x[5]; o->t[2] = x[6];
+  // dF/dq_c: F = I + 2w[u]x + 2([u]x)^2
+  double M[4][9];
+  const double u[3] = {qx, qy, qz};
+  const double U[9] = {0, -qz, qy, qz, 0, -qx, -qy, qx, 0};
+  for (int i = 0; i < 9; ++i) M[3][i] = 2.0 * U[i];                      // d/dw
+  for (int c = 0; c < 3; ++c) {
+    double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int a = (c + 1) % 3, b = (c + 2) % 3;
+    E[3 * b + a] = 1.0; E[3 * a + b] = -1.0;                             // [e_c]x
+    double EU[9], UE[9]; matmul(E, U, EU); matmul(U, E, UE);
+    for (int i = 0; i < 9; ++i) M[c][i] = 2.0 * qw * E[i] + 2.0 * (EU[i] + UE[i]);
+  }
+  (void)u;
+  double Pq[4][6], Pt[3][6];
+  for (int r = 0; r < 4; ++r) for (int j = 0; j < 6; ++j) Pq[r][j] = 0.0;
+  for (int r = 0; r < 3; ++r) for (int j = 0; j < 6; ++j) Pt[r][j] = 0.0;
+  if (param == PARAM_QUAT) {   // EigenQuaternionParameterization::ComputeJacobian (eigen_quaternion.h:108-114), rows xyzw; t additive
+    Pq[0][0] = qw;  Pq[0][1] = qz;  Pq[0][2] = -qy;
+    Pq[1][0] = -qz; Pq[1][1] = qw;  Pq[1][2] = qx;
+    Pq[2][0] = qy;  Pq[2][1] = -qx; Pq[2][2] = qw;
+    Pq[3][0] = -qx; Pq[3][1] = -qy; Pq[3][2] = -qz;
+    for (int i = 0; i < 3; ++i) Pt[i][3 + i] = 1.0;
+  } else {                     // SophusSE3Plus differentiated through x * exp(delta) INCLUDING the renormalisation
+                               // (AutoDiffLocalParameterization, the multiview default: sophus_se3.h:64-68, icp-ceres.h:42)
+    const double n2 = qx * qx + qy * qy + qz * qz + qw * qw, nn = sqrt(n2);
+    for (int i = 0; i < 3; ++i) {
+      const double h[4] = {i == 0 ? 0.5 : 0.0, i == 1 ? 0.5 : 0.0, i == 2 ? 0.5 : 0.0, 0.0};
+      double g[4]; quat_prod(x, h, g);                                   // d(q (x) q_delta)/d omega_i
+      const double dot = (g[0] * qx + g[1] * qy + g[2] * qz + g[3] * qw) / n2;
+      Pq[0][3 + i] = (g[0] - qx * dot) / nn; Pq[1][3 + i] = (g[1] - qy * dot) / nn;
+      Pq[2][3 + i] = (g[2] - qz * dot) / nn; Pq[3][3 + i] = (g[3] - qw * dot) / nn;
+      for (int r = 0; r < 3; ++r) Pt[r][i] = o->F[3 * r + i];            // d t / d upsilon_i = F e_i
+    }
+  }
+  for (int j = 0; j < 6; ++j) {
+    for (int i = 0; i < 9; ++i) o->D[j][i] = Pq[0][j] * M[0][i] + Pq[1][j] * M[1][i] + Pq[2][j] * M[2][i] + Pq[3][j] * M[3][i];
+    for (int r = 0; r < 3; ++r) o->c[j][r] = Pt[r][j];
+  }
+}
+
 }  // namespace mv
