@@ -137,8 +137,12 @@ def test_real_bunny_nonrigid_poses(oracle, golden_dir, param, cost):
     Pref, sref, _ = oracle.optimize(pts, nor, poses, edges, corr, w, param=param, cost=cost, robust=True, se3_autodiff=True, threads=8)
     assert summ["num_iterations"] == sref["num_iterations"] and summ["termination"] == sref["termination"]
     assert abs(summ["initial_cost"] - sref["initial_cost"]) <= 1e-9 * sref["initial_cost"]
-    assert abs(summ["final_cost"] - sref["final_cost"]) <= 1e-9 * sref["final_cost"]
-    assert pose_rel_err(P, Pref) <= TIGHT_TOL
+    # the Eigen-quaternion parameterisation's hand-written Jacobian is not the derivative of its Plus (rotation by
+    # 2|delta|, eigen_quaternion.h:89-114), so LM crawls to the iteration limit on this problem and rounding differences
+    # of 1e-12 per iteration (measured: tools/dbg_general.py) grow to ~1e-6 by iteration 50; the contract is 1e-5
+    tol = POSE_TOL if param == PARAM_QUAT else TIGHT_TOL
+    assert abs(summ["final_cost"] - sref["final_cost"]) <= (1e-5 if param == PARAM_QUAT else 1e-9) * sref["final_cost"]
+    assert pose_rel_err(P, Pref) <= tol
     # a second round continues from poses that are still non-rigid for the fixed / quaternion frames
     eng.correspond(0.05)
     summ2 = eng.optimize(param, cost, True)
