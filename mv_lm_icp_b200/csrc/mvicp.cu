@@ -75,7 +75,7 @@ struct mvicp_ctx {
   // graph
   int E = 0;
   std::vector<EdgeDev> h_edges;
-  DevBuf d_edges, d_xf, d_corr, d_d2, d_count, d_sel, d_hist, d_weight, d_median;
+  DevBuf d_edges, d_xf, d_corr, d_d2, d_count, d_sel, d_hist, d_weight, d_median, d_selcand, d_selcand_n;
   DevBuf d_knn_tiles, d_eval_tiles, d_edge_tile_begin, d_partial, d_blocks;
   int n_knn_tiles = 0, n_eval_tiles = 0, eval_tile_len = EVAL_TILE;
   int64_t total_slots = 0;
@@ -179,7 +179,7 @@ void mvicp_destroy(mvicp_ctx* c) {
   if (c->comm) ncclCommDestroy(c->comm);
   for (void* p : c->frame_allocs) cudaFree(p);
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
-                    &c->d_weight, &c->d_median, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
+                    &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
                     &c->d_blocks, &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
@@ -334,6 +334,8 @@ static int rebuild_work(mvicp_ctx* c) {
   RET(c->d_hist.reserve(sizeof(unsigned int) * SEL_BINS * (size_t)E));
   RET(c->d_weight.reserve(sizeof(float) * E));
   RET(c->d_median.reserve(sizeof(double) * E));
+  RET(c->d_selcand.reserve(sizeof(unsigned long long) * SEL_CAP * (size_t)E));
+  RET(c->d_selcand_n.reserve(sizeof(unsigned int) * E));
   RET(c->d_knn_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, kt.size())));
   RET(c->d_eval_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, et.size())));
   RET(c->d_edge_tile_begin.reserve(sizeof(int32_t) * (E + 1)));
@@ -345,6 +347,7 @@ static int rebuild_work(mvicp_ctx* c) {
   CU(cudaMemcpy(c->d_edge_tile_begin.p, etb.data(), sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice));
   CU(cudaMemset(c->d_hist.p, 0, sizeof(unsigned int) * SEL_BINS * (size_t)E));
   CU(cudaMemset(c->d_weight.p, 0, sizeof(float) * E));
+  CU(cudaMemset(c->d_selcand_n.p, 0, sizeof(unsigned int) * E));
   CU(cudaMemset(c->d_count.p, 0, sizeof(unsigned long long) * E));
   CU(cudaMemset(c->d_corr.p, 0xff, sizeof(int32_t) * off));   // ~0 = "no inlier, candidate 0"
   c->h_weight.assign(E, 0.f); c->h_count.assign(E, 0ull);
@@ -405,17 +408,25 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   // exact median -> weight
   select_init_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_sel.as<SelState>(), E);
   c->stats.kernel_launches += 1;
-  const int shifts[6] = {53, 42, 31, 20, 9, 0}, nbits[6] = {11, 11, 11, 11, 11, 9};
-  for (int p = 0; p < 6; ++p) {
+  const int shifts[2] = {53, 42};
+  for (int p = 0; p < 2; ++p) {
     if (c->n_eval_tiles)
       select_hist_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(
           c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len, c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
-          c->d_sel.as<SelState>(), shifts[p], nbits[p], c->d_hist.as<unsigned int>());
-    select_pick_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_hist.as<unsigned int>(), shifts[p], p == 0, p == 5,
+          c->d_sel.as<SelState>(), shifts[p], 11, c->d_hist.as<unsigned int>());
+    select_pick_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_hist.as<unsigned int>(), shifts[p], p == 0, 0,
                                                          c->d_weight.as<float>(), c->d_median.as<double>(),
                                                          c->d_count.as<unsigned long long>());
     c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
   }
+  if (c->n_eval_tiles)
+    select_collect_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(
+        c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len, c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
+        c->d_sel.as<SelState>(), c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>());
+  select_finish_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
+                                                         c->d_sel.as<SelState>(), c->d_selcand.as<unsigned long long>(),
+                                                         c->d_selcand_n.as<unsigned int>(), c->d_weight.as<float>(), c->d_median.as<double>());
+  c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
   CU(cudaEventRecord(c->ev[2], c->stream));
   CU(cudaGetLastError());
   return MVICP_OK;

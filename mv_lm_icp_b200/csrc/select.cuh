@@ -4,7 +4,10 @@
 // to float (src/internal/frame.cpp:166-176).  dists = sqrt(d2) and sqrt is monotone, so the element at sorted
 // position size/2 of the distances is the sqrt of the element at that position of the squared distances.
 // Non-negative doubles order like their bit patterns => an MSB-first radix select over the 64-bit patterns
-// gives the exact order statistic (6 passes of 11/11/11/11/11/9 bits, shared-memory histograms).
+// gives the exact order statistic.  Two full histogram passes (bits 63:53, 52:42; the first also counts the inliers)
+// narrow each edge to the values sharing a 22-bit prefix -- a few hundred out of 200 k -- which one more pass collects
+// into a small buffer; a final one-block-per-edge kernel finishes the remaining 42 bits on that buffer in shared memory
+// (or, if an edge's bucket overflows the buffer -- masses of near-equal distances -- by scanning the edge itself).
 #pragma once
 #include <cuda_runtime.h>
 #include "types.cuh"
@@ -95,6 +98,83 @@ select_pick_kernel(SelState* __restrict__ st, unsigned int* __restrict__ hist, i
     if (st[e].count == 0) { weight[e] = 0.0f; median[e] = __longlong_as_double(0x7ff8000000000000LL); }
     else {
       const double nth = __dsqrt_rn(__longlong_as_double((long long)st[e].prefix));
+      median[e] = nth;
+      weight[e] = __double2float_rn(__dmul_rn(nth, 1.5));
+    }
+  }
+}
+
+
+constexpr int SEL_CAP = 4096;   // collected candidates per edge
+
+// append the keys that match the 22-bit prefix to the edge's candidate buffer
+__global__ void __launch_bounds__(SEL_THREADS)
+select_collect_kernel(const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles, int tile_len,
+                      const int32_t* __restrict__ corr, const double* __restrict__ d2, const SelState* __restrict__ st,
+                      unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_n) {
+  const Tile t = tiles[blockIdx.x];
+  const EdgeDev e = edges[t.edge];
+  const unsigned long long prefix = st[t.edge].prefix >> 42;
+  const int end = min(t.start + tile_len, e.n_src);
+  for (int k = t.start + threadIdx.x; k < end; k += blockDim.x) {
+    if (corr[e.off + k] < 0) continue;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(d2[e.off + k]);
+    if ((key >> 42) != prefix) continue;
+    const unsigned int slot = atomicAdd(&cand_n[t.edge], 1u);
+    if (slot < SEL_CAP) cand[(size_t)t.edge * SEL_CAP + slot] = key;
+  }
+}
+
+// one block per edge: the remaining digits (41:31, 30:20, 19:9, 8:0) over the candidates -> exact median -> weight
+__global__ void __launch_bounds__(SEL_THREADS)
+select_finish_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ corr, const double* __restrict__ d2,
+                     SelState* __restrict__ st, const unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_n,
+                     float* __restrict__ weight, double* __restrict__ median) {
+  const int e = blockIdx.x;
+  __shared__ unsigned int sh[SEL_BINS];
+  __shared__ unsigned long long s_prefix, s_rank;
+  const unsigned int nc = cand_n[e];
+  const bool overflow = nc > SEL_CAP;
+  const EdgeDev ed = edges[e];
+  if (threadIdx.x == 0) { s_prefix = st[e].prefix; s_rank = st[e].rank; }
+  __syncthreads();
+  const int shifts[4] = {31, 20, 9, 0}, nbits[4] = {11, 11, 11, 9};
+  if (st[e].count != 0) {
+    for (int p = 0; p < 4; ++p) {
+      for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) sh[i] = 0u;
+      __syncthreads();
+      const int shift = shifts[p], hi = shift + nbits[p];
+      const unsigned int mask = (1u << nbits[p]) - 1u;
+      const unsigned long long prefix = s_prefix;
+      if (!overflow) {
+        for (unsigned int i = threadIdx.x; i < nc; i += blockDim.x) {
+          const unsigned long long key = cand[(size_t)e * SEL_CAP + i];
+          if ((key >> hi) == (prefix >> hi)) atomicAdd(&sh[(unsigned int)(key >> shift) & mask], 1u);
+        }
+      } else {   // rare: more equal-prefix values than the buffer holds -- scan the edge itself
+        for (int k = threadIdx.x; k < ed.n_src; k += blockDim.x) {
+          if (corr[ed.off + k] < 0) continue;
+          const unsigned long long key = (unsigned long long)__double_as_longlong(d2[ed.off + k]);
+          if ((key >> hi) == (prefix >> hi)) atomicAdd(&sh[(unsigned int)(key >> shift) & mask], 1u);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long acc = 0; const unsigned long long rank = s_rank;
+        for (int b = 0; b < (1 << nbits[p]); ++b) {
+          if (rank < acc + sh[b]) { s_prefix = prefix | ((unsigned long long)b << shift); s_rank = rank - acc; break; }
+          acc += sh[b];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    cand_n[e] = 0u;   // ready for the next round
+    st[e].prefix = s_prefix; st[e].rank = s_rank;
+    if (st[e].count == 0) { weight[e] = 0.0f; median[e] = __longlong_as_double(0x7ff8000000000000LL); }
+    else {
+      const double nth = __dsqrt_rn(__longlong_as_double((long long)s_prefix));
       median[e] = nth;
       weight[e] = __double2float_rn(__dmul_rn(nth, 1.5));
     }

@@ -104,6 +104,24 @@ def test_edge_cases(oracle):
     eng.close(); eng2.close()
 
 
+def test_median_with_masses_of_near_equal_distances(oracle):
+    """6000 query points on a thin spherical shell around a one-point dst cloud: every squared distance shares its
+    leading 22 bits, which overflows the median select's candidate buffer and takes its scan-the-edge path; plus an
+    all-equal case (exact ties in the order statistic)."""
+    rng = np.random.default_rng(9)
+    u = rng.normal(size=(6000, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    shell = (u * (0.01 * (1 + rng.uniform(0, 1e-5, size=(6000, 1))))).astype(np.float32).astype(np.float64)
+    same = np.tile(np.array([[0.0078125, 0.0, 0.0]]), (5000, 1))
+    dst = np.zeros((1, 3))
+    pts = [dst, shell, same]
+    edges = [(1, 0), (2, 0)]
+    eng = Engine(); eng.set_frames(pts, None); eng.set_graph(edges); eng.set_poses([np.eye(4)] * 3)
+    eng.correspond(0.05)
+    ref = oracle_correspond(oracle, pts, [np.eye(4)] * 3, edges, kind="brute")
+    _check_edges(eng, ref, edges)
+    eng.close()
+
+
 def test_closest_point_api(oracle):
     sc = scene(4, 5000, 21)
     eng = Engine(); eng.set_frames(sc["pts"], sc["nor"])
