@@ -132,7 +132,9 @@ select_finish_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restric
                      float* __restrict__ weight, double* __restrict__ median) {
   const int e = blockIdx.x;
   __shared__ unsigned int sh[SEL_BINS];
-  __shared__ unsigned long long s_prefix, s_rank;
+  __shared__ unsigned int part[SEL_THREADS];
+  __shared__ int s_bin;
+  __shared__ unsigned long long s_prefix, s_rank, s_before;
   const unsigned int nc = cand_n[e];
   const bool overflow = nc > SEL_CAP;
   const EdgeDev ed = edges[e];
@@ -159,11 +161,25 @@ select_finish_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restric
         }
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        unsigned long long acc = 0; const unsigned long long rank = s_rank;
-        for (int b = 0; b < (1 << nbits[p]); ++b) {
-          if (rank < acc + sh[b]) { s_prefix = prefix | ((unsigned long long)b << shift); s_rank = rank - acc; break; }
-          acc += sh[b];
+      {   // two-level scan: 8 bins per thread, 256 partial sums scanned by one thread
+        constexpr int PER = SEL_BINS / SEL_THREADS;
+        unsigned int sum = 0;
+        for (int i = 0; i < PER; ++i) sum += sh[threadIdx.x * PER + i];
+        part[threadIdx.x] = sum;
+        if (threadIdx.x == 0) s_bin = -1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          unsigned long long acc = 0; const unsigned long long rank = s_rank;
+          for (int q = 0; q < SEL_THREADS; ++q) { if (rank < acc + part[q]) { s_bin = q; s_before = acc; break; } acc += part[q]; }
+        }
+        __syncthreads();
+        if (s_bin == (int)threadIdx.x) {
+          unsigned long long acc = s_before; const unsigned long long rank = s_rank;
+          for (int i = 0; i < PER; ++i) {
+            const unsigned int hcount = sh[threadIdx.x * PER + i];
+            if (rank < acc + hcount) { s_prefix = prefix | ((unsigned long long)(threadIdx.x * PER + i) << shift); s_rank = rank - acc; break; }
+            acc += hcount;
+          }
         }
       }
       __syncthreads();
