@@ -122,15 +122,17 @@ def test_real_bunny_nonrigid_poses(oracle, golden_dir, param, cost):
     """BASELINE config 1: the reference's own scans with their sample poses, which are NOT rigid (singular values
     1, 0.9957, 0.9957; SURVEY section 7).  The reference then runs its quaternion / SE3 functors on non-unit quaternions;
     the oracle restates that arithmetic and the engine's general LM path must reproduce it.  Three frames so that a
-    free dst frame (s,k / k,k blocks) is exercised too: [8-point dummy fixed at identity, scan 0, scan 1]."""
+    free dst frame (s,k / k,k blocks) is exercised too: scan 0 (fixed), scan 1, and scan 0 again under a slightly
+    moved copy of its (non-rigid) pose; every free frame is tied to the fixed one, so the poses are determined."""
     g = np.load(f"{golden_dir}/bunny_pair.npz")
-    pts = [g["pts0"][:8], g["pts0"], g["pts1"]]; nor = [g["nor0"][:8], g["nor0"], g["nor1"]]
-    poses = np.stack([np.eye(4), g["pose0"], g["pose1"]])
-    edges = [(1, 2), (2, 1)]
+    pts = [g["pts0"], g["pts1"], g["pts0"][::2].copy()]; nor = [g["nor0"], g["nor1"], g["nor0"][::2].copy()]
+    bump = np.eye(4); bump[:3, :3] = np.array([[1, -0.004, 0.003], [0.004, 1, -0.002], [-0.003, 0.002, 1]]); bump[:3, 3] = [0.002, -0.001, 0.0015]
+    poses = np.stack([g["pose0"], g["pose1"], bump @ g["pose0"]])
+    edges = [(1, 0), (1, 2), (2, 1), (2, 0)]
     eng = Engine(); eng.set_frames(pts, nor); eng.set_graph(edges); eng.set_poses(poses)
     eng.correspond(0.05)
     corr, w = [], []
-    for e in range(2):
+    for e in range(len(edges)):
         f, s, d, ww = eng.get_edge(e); corr.append((f, s)); w.append(ww)
     summ = eng.optimize(param, cost, True)
     P = eng.get_poses()
