@@ -145,10 +145,18 @@ def test_real_bunny_nonrigid_poses(oracle, golden_dir, param, cost):
     tol = POSE_TOL if param == PARAM_QUAT else TIGHT_TOL
     assert abs(summ["final_cost"] - sref["final_cost"]) <= (1e-5 if param == PARAM_QUAT else 1e-9) * sref["final_cost"]
     assert pose_rel_err(P, Pref) <= tol
-    # a second round continues from poses that are still non-rigid for the fixed / quaternion frames
-    eng.correspond(0.05)
+    # a second round continues from poses that are still non-rigid for the fixed / quaternion frames (with SE3 and
+    # point-to-point the reference's renormalising Plus makes every step worse there: both sides end on the minimum
+    # trust-region radius, see tools/dbg_general.py)
+    eng.set_poses(Pref); eng.correspond(0.05)
+    corr2, w2 = [], []
+    for e in range(len(edges)):
+        f, s, d, ww = eng.get_edge(e); corr2.append((f, s)); w2.append(ww)
     summ2 = eng.optimize(param, cost, True)
-    assert summ2["termination"] in (0, 1, 2)
+    P2 = eng.get_poses()
+    Pref2, sref2, _ = oracle.optimize(pts, nor, Pref, edges, corr2, w2, param=param, cost=cost, robust=True, se3_autodiff=True, threads=8)
+    assert summ2["num_iterations"] == sref2["num_iterations"] and summ2["termination"] == sref2["termination"]
+    assert pose_rel_err(P2, Pref2) <= tol
     eng.close()
 
 
