@@ -24,7 +24,7 @@ extern "C" {
 typedef struct mvicp_ctx mvicp_ctx;
 
 enum { MVICP_OK = 0, MVICP_ERR_INVALID = 1, MVICP_ERR_CUDA = 2, MVICP_ERR_NCCL = 3, MVICP_ERR_STATE = 4,
-       MVICP_ERR_NONRIGID = 5, MVICP_ERR_NOT_OWNER = 6, MVICP_ERR_EMPTY = 7 };
+       MVICP_ERR_NONRIGID = 5 /* internal guard only: non-rigid poses are supported */, MVICP_ERR_NOT_OWNER = 6, MVICP_ERR_EMPTY = 7 };
 
 /* SE(3) parameterisations (main_multiview.cpp:158-164 dispatch; layouts SURVEY 8(b)) */
 enum { MVICP_PARAM_AA = 0,   /* ceresOptimizer_ceresAngleAxis : [wx wy wz tx ty tz]            */
