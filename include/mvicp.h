@@ -38,7 +38,8 @@ typedef struct {
   int32_t flags;        /* MVICP_FLAG_*                                                       */
   void*   stream;       /* cudaStream_t to run on (NULL: the context creates its own)         */
 } mvicp_config;
-enum { MVICP_FLAG_NO_SEED = 1      /* do not seed the NN search with the previous round's match */ };
+enum { MVICP_FLAG_NO_SEED = 1,     /* do not seed the NN search with the previous round's match */
+       MVICP_FLAG_NCCL_ONLY = 2    /* sharded LM: exchange pair matrices with ncclAllReduce instead of peer-memory stores */ };
 
 /* Ceres options that the reference sets (icp-ceres.cpp:66-89) or leaves at Ceres defaults. */
 typedef struct {

@@ -199,15 +199,50 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
 // out[e] = Hp (144) | gp (12) | cost | pad; zeros for edges this rank does not own (an all-reduce then gathers).
 constexpr int EDGE_THREADS = 64;
 constexpr int EOUT_ = 160;
+
+// Sharded runs: the per-edge result is pushed straight into every peer GPU's exchange buffer over NVLink (each edge has
+// exactly one owner, so the "all-reduce" of the pair matrices is really an all-to-all broadcast with no arithmetic and
+// no ordering issue), and the last CTA of the grid raises this rank's flag on every peer; lm_step_kernel waits for all
+// ranks' flags.  Compute and collective are one kernel; NCCL is not on the LM loop's critical path.
+constexpr int MAX_PEERS = 16;
+struct PeerTable {
+  int world, rank;
+  double* eout[MAX_PEERS];          // peer p's exchange area for the current buffer half (IPC-mapped), [E][EOUT]
+  volatile int* flags[MAX_PEERS];   // peer p's flag array: flags[p][r] = last sequence number rank r completed
+};
+
+__device__ __forceinline__ void edge_publish(const PeerTable& pt, int e, int r, double v, double* __restrict__ o) {
+  o[r] = v;
+  for (int p = 0; p < pt.world; ++p) if (p != pt.rank) pt.eout[p][(size_t)EOUT_ * e + r] = v;
+}
+// every CTA of the edge kernels ends here: fence the remote stores, count, and let the last CTA raise the flags
+__device__ __forceinline__ void edge_signal(const PeerTable& pt, int seq, unsigned int* counter) {
+  if (pt.world <= 1) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *counter = 0u;
+      __threadfence_system();
+      for (int p = 0; p < pt.world; ++p) pt.flags[p][pt.rank] = seq;
+      __threadfence_system();
+    }
+  }
+}
 __global__ void __launch_bounds__(EDGE_THREADS)
 lm_edge_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
                int nused, const Rt* __restrict__ frame_Rt, const double* __restrict__ K_eval, double* __restrict__ out,
-               const int* __restrict__ done_flag) {
+               const int* __restrict__ done_flag, PeerTable pt, int seq, unsigned int* counter) {
   if (*done_flag) return;
   const int e = blockIdx.x, tid = threadIdx.x;
   __shared__ double blk[NBLK], Q[36], AQ[36], Hcan[144], T1[144], Rt_[9];
   double* o = out + (size_t)EOUT_ * e;
-  if (!edges[e].owned) { for (int i = tid; i < EOUT_; i += EDGE_THREADS) o[i] = 0.0; return; }
+  if (!edges[e].owned) {   // NCCL mode: zeros for the sum; peer mode: the owner writes this edge into our buffer
+    if (pt.world <= 1) for (int i = tid; i < EOUT_; i += EDGE_THREADS) o[i] = 0.0;
+    edge_signal(pt, seq, counter);
+    return;
+  }
   if (tid < NBLK) {
     double v = 0.0;
     if (tid < nused) for (int t = edge_tile_begin[e]; t < edge_tile_begin[e + 1]; ++t) v += partial[(size_t)t * NBLK + tid];
@@ -305,7 +340,7 @@ lm_edge_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ ed
       const int a = r / 12, b = r - 12 * a;
       const double* Ka = a < 6 ? Ks : Kk; const int off = a < 6 ? 0 : 6;
       double v = 0; for (int m = 0; m < 6; ++m) v += Ka[6 * m + (a - off)] * T1[12 * (off + m) + b];
-      o[r] = v;
+      edge_publish(pt, e, r, v, o);
     } else if (r < 156) {
       const int a = r - 144;
       const double* bv = blk + BLK_B;
@@ -317,10 +352,11 @@ lm_edge_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ ed
         else { gm = 0; for (int i = 0; i < 6; ++i) gm -= Q[6 * i + m] * bv[i]; }
         v += Ka[6 * m + (a - off)] * gm;
       }
-      o[r] = v;
-    } else o[r] = blk[BLK_COST];
+      edge_publish(pt, e, r, v, o);
+    } else edge_publish(pt, e, r, blk[BLK_COST], o);
   }
   if (tid < 3) o[157 + tid] = 0.0;
+  edge_signal(pt, seq, counter);
 }
 
 
@@ -426,12 +462,16 @@ lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __res
 // general-path counterpart of lm_edge_kernel: the partials already are the pair matrix in the parameterisation tangent
 __global__ void __launch_bounds__(EDGE_THREADS)
 lm_edge_general_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ edge_tile_begin, const double* __restrict__ partial,
-                       double* __restrict__ out, const int* __restrict__ done_flag) {
+                       double* __restrict__ out, const int* __restrict__ done_flag, PeerTable pt, int seq, unsigned int* counter) {
   if (*done_flag) return;
   const int e = blockIdx.x, tid = threadIdx.x;
   __shared__ double blk[GBLK];
   double* o = out + (size_t)EOUT_ * e;
-  if (!edges[e].owned) { for (int i = tid; i < EOUT_; i += EDGE_THREADS) o[i] = 0.0; return; }
+  if (!edges[e].owned) {
+    if (pt.world <= 1) for (int i = tid; i < EOUT_; i += EDGE_THREADS) o[i] = 0.0;
+    edge_signal(pt, seq, counter);
+    return;
+  }
   for (int j = tid; j < 91; j += EDGE_THREADS) {
     double v = 0.0;
     for (int t = edge_tile_begin[e]; t < edge_tile_begin[e + 1]; ++t) v += partial[(size_t)t * GBLK + j];
@@ -439,11 +479,12 @@ lm_edge_general_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restr
   }
   __syncthreads();
   for (int r = tid; r < 160; r += EDGE_THREADS) {
-    if (r < 144) { const int a = r / 12, b = r - 12 * a; o[r] = blk[u12(min(a, b), max(a, b))]; }
-    else if (r < 156) o[r] = blk[78 + (r - 144)];
-    else if (r == 156) o[r] = blk[90];
+    if (r < 144) { const int a = r / 12, b = r - 12 * a; edge_publish(pt, e, r, blk[u12(min(a, b), max(a, b))], o); }
+    else if (r < 156) edge_publish(pt, e, r, blk[78 + (r - 144)], o);
+    else if (r == 156) edge_publish(pt, e, r, blk[90], o);
     else o[r] = 0.0;
   }
+  edge_signal(pt, seq, counter);
 }
 
 }  // namespace mv

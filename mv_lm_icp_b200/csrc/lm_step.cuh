@@ -32,6 +32,8 @@ struct LmWork {
   const double* eout;        // [E][EOUT]: pair matrix (144), pair gradient (12), cost at the evaluation point (summed over ranks)
   volatile int32_t* host_flag; // mapped pinned ring: (sequence << 1) | done, written at the end of every step
   int32_t seq;
+  volatile int* peer_flags;    // this rank's flag array (written by the peers' edge kernels), null when not sharded over peer memory
+  int32_t world, xseq;
   double* x;                 // [M][7] accepted point (all frames)
   double* cand;              // [M][7] evaluation point / next candidate
   Rt* Rt_eval;               // [M]
@@ -145,6 +147,15 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   if (S->done) { if (threadIdx.x == 0) { w.host_flag[w.seq & 7] = (w.seq << 1) | 1; __threadfence_system(); } return; }
   const int tid = threadIdx.x, T = blockDim.x;
   const int n = S->n, M = S->M, E = S->E, param = S->param;
+  if (w.peer_flags) {   // wait until every rank's edge kernel has delivered this iteration's pair matrices
+    if (tid < w.world) {
+      const long long t0 = clock64();
+      while (w.peer_flags[tid] - w.xseq < 0) {
+        if (clock64() - t0 > 4000000000LL) { S->nonrigid = 2; break; }   // ~2 s: a peer died; surface an error instead of hanging
+      }
+    }
+    __syncthreads();
+  }
   // dynamic shared memory: [colj (n+1) | dg (n+1) | L (n+1) x (n|1) when it fits]
   double* colj = smem; double* dg = smem + (S->n + 1);
   double* L = w.l_in_smem ? smem + 2 * (S->n + 1) : w.Lg;

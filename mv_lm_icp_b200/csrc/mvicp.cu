@@ -64,6 +64,9 @@ struct mvicp_ctx {
   int device = 0, flags = 0;
   cudaStream_t stream = nullptr; bool own_stream = false;
   int rank = 0, world = 1; ncclComm_t comm = nullptr;
+  // peer-memory exchange of the LM pair matrices (sharded runs): own buffer + IPC mappings of every peer's
+  void* xbuf = nullptr; void* peer_x[MAX_PEERS] = {}; bool p2p_ok = false; int32_t xseq = 0;
+  static constexpr int X_ECAP = 4096;   // edges the exchange buffer is sized for (2 halves x X_ECAP x EOUT doubles + flags)
   // frames
   int M = 0; bool f32 = true; bool have_normals = true;
   std::vector<int64_t> n_pts;
@@ -176,6 +179,8 @@ void mvicp_destroy(mvicp_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (int p = 0; p < MAX_PEERS; ++p) if (c->peer_x[p] && c->peer_x[p] != c->xbuf) cudaIpcCloseMemHandle(c->peer_x[p]);
+  if (c->xbuf) cudaFree(c->xbuf);
   if (c->comm) ncclCommDestroy(c->comm);
   for (void* p : c->frame_allocs) cudaFree(p);
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
@@ -671,6 +676,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   const int max_evals = opt.max_num_iterations + 2;
   for (int i = 0; i < 8; ++i) c->h_flag[i] = 0;
   c->eval_ev_used = 0;
+  const bool use_p2p = c->comm && c->world > 1 && c->p2p_ok && E <= mvicp_ctx::X_ECAP;
   int issued = 0, seen = 0;
   const int* done_flag = &w.S->done;
   auto issue = [&]() -> int {
@@ -680,15 +686,32 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     else if (c->f32) launch_eval<true>(c, cost, st.robust, done_flag); else launch_eval<false>(c, cost, st.robust, done_flag);
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used + 1], c->stream));
     c->eval_ev_used += 2;
+    // sharded: pair matrices go straight into every peer's exchange buffer (double-buffered by iteration parity)
+    PeerTable pt; std::memset(&pt, 0, sizeof pt); pt.world = 1; pt.rank = 0;
+    double* eout_local = c->d_eout.as<double>();
+    unsigned int* xcounter = nullptr;
+    int xs = 0;
+    if (use_p2p) {
+      xs = ++c->xseq;
+      const size_t half = (size_t)mvicp_ctx::X_ECAP * EOUT;
+      pt.world = c->world; pt.rank = c->rank;
+      for (int p = 0; p < c->world; ++p) {
+        pt.eout[p] = (double*)c->peer_x[p] + (size_t)(xs & 1) * half;
+        pt.flags[p] = (volatile int*)((double*)c->peer_x[p] + 2 * half);
+      }
+      eout_local = pt.eout[c->rank];
+      xcounter = (unsigned int*)((double*)c->xbuf + 2 * half) + 32;
+    }
     if (general)
       lm_edge_general_kernel<<<E, EDGE_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_edge_tile_begin.as<int32_t>(),
-                                                                c->d_partial.as<double>(), c->d_eout.as<double>(), done_flag);
+                                                                c->d_partial.as<double>(), eout_local, done_flag, pt, xs, xcounter);
     else
       lm_edge_kernel<<<E, EDGE_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_edge_tile_begin.as<int32_t>(), c->d_partial.as<double>(),
                                                         cost == COST_P2PLANE ? NBLK_PLANE : NBLK, c->d_Rt.as<Rt>(), c->d_K.as<double>(),
-                                                        c->d_eout.as<double>(), done_flag);
-    if (c->comm && c->world > 1)
+                                                        eout_local, done_flag, pt, xs, xcounter);
+    if (c->comm && c->world > 1 && !use_p2p)
       NC(ncclAllReduce(c->d_eout.p, c->d_eout.p, (size_t)EOUT * E, ncclDouble, ncclSum, c->comm, c->stream));
+    w.eout = eout_local; w.peer_flags = use_p2p ? pt.flags[c->rank] : nullptr; w.world = c->world; w.xseq = xs;
     w.seq = issued + 1;
     lm_step_kernel<<<1, STEP_THREADS, dyn, c->stream>>>(w);
     c->stats.kernel_launches += (c->n_eval_tiles ? 1 : 0) + 2;
@@ -742,6 +765,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     summary->num_evaluations = st.n_evals; summary->num_linear_solves = st.n_solves; summary->reserved = 0;
     summary->initial_cost = st.initial_cost; summary->final_cost = st.x_cost;
   }
+  if (st.nonrigid == 2) return fail(MVICP_ERR_NCCL, "a peer rank never delivered its pair matrices (peer-memory exchange timed out)");
   if (st.nonrigid && !general)   // cannot happen after mvicp_set_poses; guards poses that reached the device another way
     return fail(MVICP_ERR_NONRIGID, "a pose's quaternion is not unit (non-rigid Isometry) but the unit-quaternion LM path was run");
   if (!st.done) return fail(MVICP_ERR_STATE, "LM loop did not terminate within %d evaluations", max_evals);
@@ -795,6 +819,40 @@ int mvicp_comm_init(mvicp_ctx* c, const void* id128, int32_t rank, int32_t world
   ncclUniqueId id; std::memcpy(&id, id128, 128);
   if (world > 1) NC(ncclCommInitRank(&c->comm, world, id, rank));
   c->rank = rank; c->world = world;
+  c->p2p_ok = false;
+  if (world > 1 && world <= MAX_PEERS && !(c->flags & MVICP_FLAG_NCCL_ONLY)) {
+    // exchange buffer in this rank's memory, mapped into every peer through CUDA IPC (handles travel over NCCL)
+    const size_t xbytes = sizeof(double) * 2 * (size_t)mvicp_ctx::X_ECAP * EOUT + 256;
+    bool ok = true;
+    if (!c->xbuf) ok = cudaMalloc(&c->xbuf, xbytes) == cudaSuccess;
+    if (ok) ok = cudaMemset(c->xbuf, 0, xbytes) == cudaSuccess;
+    cudaIpcMemHandle_t mine; std::memset(&mine, 0, sizeof mine);
+    if (ok) ok = cudaIpcGetMemHandle(&mine, c->xbuf) == cudaSuccess;
+    void* d_h = nullptr;
+    std::vector<cudaIpcMemHandle_t> all(world);
+    int32_t okflag = ok ? 1 : 0;
+    if (cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (world + 1) + 64) != cudaSuccess) return fail(MVICP_ERR_CUDA, "comm_init: cudaMalloc");
+    char* dh = (char*)d_h;
+    CU(cudaMemcpy(dh, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NC(ncclAllGather(dh, dh + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t), ncclUint8, c->comm, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(all.data(), dh + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t) * world, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < world && ok; ++p) {
+      if (p == rank) { c->peer_x[p] = c->xbuf; continue; }
+      if (!c->peer_x[p]) ok = cudaIpcOpenMemHandle(&c->peer_x[p], all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    cudaGetLastError();
+    // every rank must agree, or the flag protocol would wait for a rank that took the NCCL path
+    okflag = ok ? 1 : 0;
+    int32_t* d_ok = (int32_t*)(dh + sizeof(cudaIpcMemHandle_t) * (world + 1));
+    CU(cudaMemcpy(d_ok, &okflag, sizeof okflag, cudaMemcpyHostToDevice));
+    NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(&okflag, d_ok, sizeof okflag, cudaMemcpyDeviceToHost));
+    cudaFree(d_h);
+    c->p2p_ok = okflag == 1;
+    c->xseq = 0;
+  }
   return rebuild_work(c);
 }
 
