@@ -60,6 +60,17 @@ struct Session {
   }
 };
 
+// Frame::recomputeNormals for every frame (frame.cpp:244-255; loadFrames calls it per frame, main_multiview.cpp:68).
+template <class FrameT>
+void recomputeNormals(Session<FrameT>& s, std::vector<std::shared_ptr<FrameT>>& frames, int k = 10) {
+  s.bind(frames);
+  check(mvicp_recompute_normals(s.ctx, k));
+  for (size_t i = 0; i < frames.size(); ++i) {
+    frames[i]->nor.resize(frames[i]->pts.size());
+    check(mvicp_get_normals(s.ctx, (int32_t)i, frames[i]->nor[0].data(), nullptr));
+  }
+}
+
 // ApproachComponents::computeClosestPoints (main_multiview.cpp:119-127).  materialize = fill OutgoingEdge::correspondances
 // on the host (the viewer reads them, Visualize.cpp:470-479); the optimiser itself never needs them on the host.
 template <class FrameT>

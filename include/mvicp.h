@@ -141,6 +141,13 @@ int mvicp_pairwise(const mvicp_config* cfg, int32_t param, int32_t cost, const d
                    const double* nor_xyz, int64_t n, const mvicp_lm_options* opt, double* pose16_out,
                    mvicp_lm_summary* summary);
 
+/* Frame::recomputeNormals for every frame (frame.cpp:244-255; default-on in main_multiview.cpp:49,68): k nearest
+ * neighbours of each point in its own cloud (the point included; the reference uses k = 10) + pointSetPCA
+ * (common.h:331-346).  The new normals replace the uploaded ones for mvicp_optimize; mvicp_get_normals copies them back
+ * (N x 3 doubles) so that the caller can store them in Frame::nor. */
+int mvicp_recompute_normals(mvicp_ctx* ctx, int32_t k);
+int mvicp_get_normals(mvicp_ctx* ctx, int32_t frame, double* nor_xyz, float* elapsed_ms /*nullable: device time of the recompute*/);
+
 /* ---- multi-GPU: one process per GPU, frames sharded by owner = frame * world / n_frames ------------------ */
 int mvicp_nccl_unique_id(void* out128);   /* rank 0 creates, the launcher broadcasts the 128 bytes */
 int mvicp_comm_init(mvicp_ctx* ctx, const void* id128, int32_t rank, int32_t world_size);

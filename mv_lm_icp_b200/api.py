@@ -142,6 +142,16 @@ class Engine:
                                       C.c_int32(int(robust)), C.byref(options) if options is not None else None, C.byref(s)))
         return s.asdict()
 
+    def recompute_normals(self, k=10):
+        """Frame::recomputeNormals for every frame (frame.cpp:244-255). Returns (list of [N,3] normals, device ms)."""
+        check(self._l.mvicp_recompute_normals(self._ctx, C.c_int32(k)))
+        out = []; ms = C.c_float(0)
+        for f in range(self.M):
+            nor = np.empty((self.n_pts[f], 3))
+            check(self._l.mvicp_get_normals(self._ctx, C.c_int32(f), _p(nor), C.byref(ms)))
+            out.append(nor)
+        return out, ms.value
+
     # ---- multi-GPU / introspection ---------------------------------------------------------------------
     def comm_init(self, unique_id, rank, world):
         check(self._l.mvicp_comm_init(self._ctx, C.c_char_p(unique_id), C.c_int32(rank), C.c_int32(world)))
@@ -207,6 +217,11 @@ class ICP_Ceres:
         P = self.engine.get_poses()
         for i, f in enumerate(self.frames):
             f.pose = P[i]
+
+    def recomputeNormals(self, k=10):   # Frame::recomputeNormals, main_multiview.cpp:68
+        nor, _ = self.engine.recompute_normals(k)
+        for f, n in zip(self.frames, nor):
+            f.nor = n
 
     def computePoseNeighbours(self, knn):   # main_multiview.cpp:104-117
         self._push_poses()

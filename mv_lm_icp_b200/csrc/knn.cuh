@@ -66,7 +66,8 @@ __device__ __forceinline__ void nn_tighten(NNQuery& s) {
   s.bound32 = __fmul_ru(__fmaf_ru(s.eaf, __fmaf_ru(2.0f, r, s.eaf), b), 1.000001f);
 }
 
-__device__ __forceinline__ float box_lb32(const Box* __restrict__ boxes, int node, const NNQuery& s) {
+template <class Q>
+__device__ __forceinline__ float box_lb32(const Box* __restrict__ boxes, int node, const Q& s) {
   const float4* b = reinterpret_cast<const float4*>(boxes + node);
   const float4 u = __ldg(b), v = __ldg(b + 1);   // u = lo.xyz, hi.x ; v = hi.yz
   const float dx = fmaxf(fmaxf(u.x - s.fx, s.fx - u.w), 0.f);
@@ -85,14 +86,15 @@ __device__ __forceinline__ void nn_exact(const FrameDev& fd, int64_t pos, const 
   if (d < s.best || (d == s.best && pi < s.bi)) { s.best = d; s.bi = pi; nn_tighten(s); }
 }
 
-__device__ __forceinline__ float pt_d32(const float4& r, const NNQuery& s) {
+template <class Q>
+__device__ __forceinline__ float pt_d32(const float4& r, const Q& s) {
   const float dx = s.fx - r.x, dy = s.fy - r.y, dz = s.fz - r.z;
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
 // two points of a leaf per step (the point arrays are padded with +inf up to a multiple of LEAF)
-template <bool F32>
-__device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int sub, NNQuery& s) {
+template <bool F32, class Q>
+__device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int sub, Q& s) {
   const int64_t pos = (int64_t)leaf * LEAF + 2 * sub;
   const float4 r0 = __ldg(fd.pts_sf + pos), r1 = __ldg(fd.pts_sf + pos + 1);
   const float d0 = pt_d32(r0, s), d1 = pt_d32(r1, s);
@@ -107,14 +109,14 @@ __device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int s
 // points of a leaf (a leaf takes LEAF/2 steps) -- so that the lanes of a warp, which sit at different nodes, still
 // execute the same instructions; only the trip count differs between lanes.
 constexpr int NN_STACK = 64;   // >= 2 * depth: flagged siblings + far children of one descent
-template <bool F32>
-__device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int start_leaf) {
+template <bool F32, class Q>
+__device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_leaf) {
   const int L = fd.n_leaf_pad;
   int leaf_node = -1;
   if (start_leaf >= 0) {
     leaf_node = L + start_leaf;
 #pragma unroll
-    for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32>(fd, start_leaf, sub, s);
+    for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, start_leaf, sub, s);
     // a stale guess (the poses moved a lot since it was made) leaves a loose bound, and everything inside that ball
     // would be visited on the way up: if the guess is further than a few leaf sizes, descend greedily instead
     const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
@@ -131,7 +133,7 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
     }
     if (node != leaf_node) {
 #pragma unroll
-      for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32>(fd, node - L, sub, s);
+      for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, node - L, sub, s);
     }
     leaf_node = node;
   }
@@ -158,7 +160,7 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, NNQuery& s, int st
       node = stk_n[sp]; sub = 0;
     }
     if (node >= L) {
-      nn_leaf_step<F32>(fd, node - L, sub, s);
+      nn_leaf_step<F32, Q>(fd, node - L, sub, s);
       if (++sub == LEAF / 2) node = -1;
     } else {
       const int c0 = 2 * node;
@@ -220,7 +222,7 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
       const int si = sd >= 0 ? sd : ~sd;
       if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
     }
-    nn_search<F32>(fd, nq, start_leaf);
+    nn_search<F32, NNQuery>(fd, nq, start_leaf);
     const double best = nq.best; const int bi = nq.bi;
     const bool inlier = __dsqrt_rn(best) < thresh;
     corr[e.off + orig] = inlier ? bi : ~bi;
@@ -233,7 +235,7 @@ __global__ void knn_single_kernel(const FrameDev* __restrict__ frames, int frame
                                   long long* out_idx, double* out_d2) {
   const FrameDev fd = frames[frame];
   NNQuery nq; nn_query_init(nq, qx, qy, qz, fd.absmax);
-  nn_search<F32>(fd, nq, -1);
+  nn_search<F32, NNQuery>(fd, nq, -1);
   *out_idx = nq.bi; *out_d2 = nq.best;
 }
 

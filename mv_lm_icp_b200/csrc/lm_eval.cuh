@@ -47,7 +47,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // partial[tile][NBLK]: layout BLK_* of types.cuh
-template <bool F32, int COST>
+template <bool F32, bool NF32, int COST>
 __global__ void __launch_bounds__(EVAL_THREADS, 2)
 lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
                int tile_len, const int32_t* __restrict__ corr, const Rt* __restrict__ frame_Rt,
@@ -93,13 +93,14 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
       const int k = k0 + u * EVAL_THREADS;
       cidx[u] = (k < end) ? __ldg(corr + e.off + k) : -1;
     }
-    rec_t P[U], Q[U], Nn[U];
+    typedef typename Rec<NF32>::type nrec_t;   // normals keep fp32 records only while they are fp32-exact (not after mvicp_recompute_normals)
+    rec_t P[U], Q[U]; nrec_t Nn[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (cidx[u] >= 0) {
         P[u] = rec_load<F32>(fs.pts_o, k0 + u * EVAL_THREADS);
         Q[u] = rec_load<F32>(fd.pts_o, cidx[u]);
-        if (COST != COST_P2P) Nn[u] = rec_load<F32>(fd.nor_o, cidx[u]);
+        if (COST != COST_P2P) Nn[u] = rec_load<NF32>(fd.nor_o, cidx[u]);
       }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -368,7 +369,7 @@ lm_edge_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ ed
 constexpr int GBLK = 96;   // stride of a general partial: 78 (upper 12x12) | 12 | 1
 __device__ __forceinline__ int u12(int i, int j) { return i * 12 - (i * (i - 1)) / 2 + (j - i); }
 
-template <bool F32, int COST, int PASS>
+template <bool F32, bool NF32, int COST, int PASS>
 __global__ void __launch_bounds__(EVAL_THREADS)
 lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
                        int tile_len, const int32_t* __restrict__ corr, const FrameGen* __restrict__ frame_gen,
@@ -399,7 +400,7 @@ lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __res
     double p[3], q[3], n[3] = {0, 0, 0}; int dummy;
     Rec<F32>::load(fs.pts_o, k, p[0], p[1], p[2], dummy);
     Rec<F32>::load(fd.pts_o, c, q[0], q[1], q[2], dummy);
-    if (COST != COST_P2P) Rec<F32>::load(fd.nor_o, c, n[0], n[1], n[2], dummy);
+    if (COST != COST_P2P) Rec<NF32>::load(fd.nor_o, c, n[0], n[1], n[2], dummy);
     double ys[3], yk[3], n2[3], d[3];
     matvec(gs.F, p, ys); matvec(gk.F, q, yk); matvec(gk.F, n, n2);
     for (int i = 0; i < 3; ++i) d[i] = (ys[i] + gs.t[i]) - (yk[i] + gk.t[i]);

@@ -21,6 +21,7 @@
 #include "knn.cuh"
 #include "lm_eval.cuh"
 #include "lm_step.cuh"
+#include "normals.cuh"
 #include "se3_math.cuh"
 #include "select.cuh"
 #include "types.cuh"
@@ -68,7 +69,9 @@ struct mvicp_ctx {
   void* xbuf = nullptr; void* peer_x[MAX_PEERS] = {}; bool p2p_ok = false; int32_t xseq = 0;
   static constexpr int X_ECAP = 4096;   // edges the exchange buffer is sized for (2 halves x X_ECAP x EOUT doubles + flags)
   // frames
-  int M = 0; bool f32 = true; bool have_normals = true;
+  int M = 0; bool f32 = true; bool nor_f32 = true; bool have_normals = true;
+  std::vector<void*> nor_dbl;   // per frame: fp64 normals [n][3] after mvicp_recompute_normals (device)
+  float normals_ms = 0.f;
   std::vector<int64_t> n_pts;
   std::vector<FrameDev> h_frames;
   std::vector<void*> frame_allocs;
@@ -215,7 +218,7 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     if (!nor || !nor[f]) c->have_normals = false;
     f32 = f32 && all_fp32(pts[f], 3 * n_pts[f]) && (!nor || !nor[f] || all_fp32(nor[f], 3 * n_pts[f]));
   }
-  c->f32 = f32;
+  c->f32 = f32; c->nor_f32 = f32; c->nor_dbl.clear();
   const size_t rec = f32 ? sizeof(float4) : sizeof(double4a);
   std::vector<HostFrameBuild> builds(M);
   {
@@ -549,11 +552,13 @@ static int prepare_lm(mvicp_ctx* c, int n) {
 template <bool F32> static void launch_eval(mvicp_ctx* c, int cost, int robust, const int* done_flag) {
   const int nt = c->n_eval_tiles;
   if (!nt) return;
-#define MV_EVAL(COSTK)                                                                                           \
-  lm_eval_kernel<F32, COSTK><<<nt, EVAL_THREADS, 0, c->stream>>>(                                                \
+#define MV_EVAL(NF, COSTK)                                                                                       \
+  lm_eval_kernel<F32, NF, COSTK><<<nt, EVAL_THREADS, 0, c->stream>>>(                                            \
       c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
       c->d_corr.as<int32_t>(), c->d_Rt.as<Rt>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag)
-  if (cost == COST_P2P) MV_EVAL(COST_P2P); else if (cost == COST_P2PLANE) MV_EVAL(COST_P2PLANE); else MV_EVAL(COST_MIXED);
+#define MV_EVALC(NF) { if (cost == COST_P2P) MV_EVAL(NF, COST_P2P); else if (cost == COST_P2PLANE) MV_EVAL(NF, COST_P2PLANE); else MV_EVAL(NF, COST_MIXED); }
+  if (F32 && c->nor_f32) MV_EVALC(F32) else MV_EVALC(false)
+#undef MV_EVALC
 #undef MV_EVAL
 }
 
@@ -561,7 +566,10 @@ template <bool F32> static void launch_eval_general(mvicp_ctx* c, int cost, int 
   const int nt = c->n_eval_tiles;
   if (!nt) return;
 #define MV_EVALG(COSTK, PASSK)                                                                                   \
-  lm_eval_general_kernel<F32, COSTK, PASSK><<<nt, EVAL_THREADS, 0, c->stream>>>(                                 \
+  if (F32 && c->nor_f32) lm_eval_general_kernel<F32, F32, COSTK, PASSK><<<nt, EVAL_THREADS, 0, c->stream>>>(     \
+      c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
+      c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag); \
+  else lm_eval_general_kernel<F32, false, COSTK, PASSK><<<nt, EVAL_THREADS, 0, c->stream>>>(                     \
       c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
       c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag)
 #define MV_EVALG3(COSTK) { MV_EVALG(COSTK, 0); MV_EVALG(COSTK, 1); MV_EVALG(COSTK, 2); }
@@ -801,6 +809,46 @@ int mvicp_pairwise(const mvicp_config* cfg, int32_t param, int32_t cost, const d
   mvicp_destroy(c);
   g_err = keep;
   return rc;
+}
+
+// ---- normal estimation ---------------------------------------------------------------
+int mvicp_recompute_normals(mvicp_ctx* c, int32_t k) {
+  if (!c || !c->M) return fail(MVICP_ERR_STATE, "mvicp_recompute_normals: frames must be set first");
+  if (k < 3 || k > KNN_MAXK) return fail(MVICP_ERR_INVALID, "mvicp_recompute_normals: k must be in [3, %d] (pointSetPCA asserts >= 3)", KNN_MAXK);
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  c->nor_dbl.resize(c->M, nullptr);
+  cudaEvent_t e0 = c->ev[5], e1 = c->ev[6];
+  CU(cudaEventRecord(e0, c->stream));
+  for (int f = 0; f < c->M; ++f) {
+    const int n = (int)c->n_pts[f];
+    if (!c->nor_dbl[f]) { CU(cudaMalloc(&c->nor_dbl[f], sizeof(double) * 3 * (size_t)n)); c->frame_allocs.push_back(c->nor_dbl[f]); }
+    if (c->f32) normals_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, k, (double*)c->nor_dbl[f], nullptr);
+    else normals_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, k, (double*)c->nor_dbl[f], nullptr);
+    // the LM kernels gather normals as records: recomputed normals are not fp32-exact, so they become 32-byte fp64 records
+    void* rec = nullptr;
+    if (c->nor_f32 || !c->h_frames[f].nor_o) { CU(cudaMalloc(&rec, sizeof(double4a) * (size_t)n)); c->frame_allocs.push_back(rec); }
+    else rec = const_cast<void*>(c->h_frames[f].nor_o);
+    pack_normals_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const double*)c->nor_dbl[f], n, (double4a*)rec);
+    c->h_frames[f].nor_o = rec;
+    c->stats.kernel_launches += 2;
+  }
+  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaMemcpyAsync(c->d_frames.p, c->h_frames.data(), sizeof(FrameDev) * c->M, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  cudaEventElapsedTime(&c->normals_ms, e0, e1);
+  c->nor_f32 = false; c->have_normals = true;
+  return MVICP_OK;
+}
+
+int mvicp_get_normals(mvicp_ctx* c, int32_t frame, double* nor_xyz, float* elapsed_ms) {
+  if (!c || frame < 0 || frame >= c->M || !nor_xyz) return fail(MVICP_ERR_INVALID, "mvicp_get_normals: bad arguments");
+  if ((int)c->nor_dbl.size() <= frame || !c->nor_dbl[frame]) return fail(MVICP_ERR_STATE, "mvicp_get_normals: call mvicp_recompute_normals first");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(nor_xyz, c->nor_dbl[frame], sizeof(double) * 3 * (size_t)c->n_pts[frame], cudaMemcpyDeviceToHost));
+  if (elapsed_ms) *elapsed_ms = c->normals_ms;
+  return MVICP_OK;
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------------------

@@ -127,6 +127,27 @@ class KdIndex:
         return idx, d2
 
 
+def recompute_normals(pts, k=10, threads=1, want_nn=False):
+    """Restated Frame::recomputeNormals (frame.cpp:244-255, common.h:331-346). Returns normals [N,3] (and the k-NN indices)."""
+    pts = _f64(pts).reshape(-1, 3)
+    n = len(pts)
+    nor = np.empty((n, 3)); nn = np.empty((n, k), np.int32)
+    lib().orc_recompute_normals(_p(pts), C.c_int64(n), C.c_int(k), _p(nor), _p(nn, C.c_int32) if want_nn else None, C.c_int(threads))
+    return (nor, nn) if want_nn else nor
+
+
+def knn(index, q, k):
+    """k nearest neighbours of q in a KdIndex ('kd' oracle restatement or 'ref' = the reference's nanoflann knnSearch)."""
+    q = _f64(q)
+    if index.kind == "ref":
+        idx = np.empty(k, np.int64); d2 = np.empty(k)
+        ref_lib().ref_kd_knn(index.h, _p(q), C.c_int64(k), _p(idx, C.c_int64), _p(d2))
+        return idx.astype(np.int32), d2
+    idx = np.empty(k, np.int32); d2 = np.empty(k)
+    lib().orc_kd_knn(index.h, _p(q), C.c_int(k), _p(idx, C.c_int32), _p(d2))
+    return idx, d2
+
+
 def edge_queries(src_pts, pose_src, pose_dst):
     src = _f64(src_pts).reshape(-1, 3)
     ps = _f64(np.asarray(pose_src).T).reshape(16)

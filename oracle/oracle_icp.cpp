@@ -129,6 +129,28 @@ struct KdTree {
     if (lf <= best) search(first, q, best, bi);
     if (ls <= best) search(second, q, best, bi);
   }
+  // k nearest (ascending distance; equal distances by ascending index) -- Frame::getNeighbours' knnSearch (frame.cpp:208-225)
+  void knn_rec(int32_t ni, const double* q, int k, std::vector<std::pair<double, int32_t>>& heap) const {
+    const Node& nd = nodes[ni];
+    const double worst = (int)heap.size() < k ? std::numeric_limits<double>::infinity() : heap.back().first;
+    if (nd.left < 0) {
+      for (int32_t i = nd.begin; i < nd.end; ++i) {
+        const int32_t j = idx[i];
+        const std::pair<double, int32_t> c{dist_sq(q, pts + 3 * (int64_t)j), j};
+        if ((int)heap.size() < k || c < heap.back()) {
+          heap.insert(std::upper_bound(heap.begin(), heap.end(), c), c);
+          if ((int)heap.size() > k) heap.pop_back();
+        }
+      }
+      return;
+    }
+    (void)worst;
+    const double ll = box_lb(nodes[nd.left], q), lr = box_lb(nodes[nd.right], q);
+    const int32_t first = ll <= lr ? nd.left : nd.right, second = ll <= lr ? nd.right : nd.left;
+    const double lf = ll <= lr ? ll : lr, ls = ll <= lr ? lr : ll;
+    if ((int)heap.size() < k || lf <= heap.back().first) knn_rec(first, q, k, heap);
+    if ((int)heap.size() < k || ls <= heap.back().first) knn_rec(second, q, k, heap);
+  }
   void query(const double* q, int32_t* out_idx, double* out_d2) const {
     double best = std::numeric_limits<double>::infinity(); int32_t bi = std::numeric_limits<int32_t>::max();
     if (n > 0) search(0, q, best, bi);
@@ -466,6 +488,65 @@ void orc_pose_graph_knn(int M, const double* poses16, int knn, int32_t* out_dst,
       out_dst[i * knn + q] = q < (int)nb.size() ? nb[q].second : -1;
       if (out_w) out_w[i * knn + q] = q < (int)nb.size() ? nb[q].first : 0.f;
     }
+  }
+}
+
+// k nearest neighbours of a query in the index's own frame
+void orc_kd_knn(void* h, const double* q, int k, int32_t* idx, double* d2) {
+  std::vector<std::pair<double, int32_t>> heap;
+  const KdTree* T = (const KdTree*)h;
+  if (T->n > 0) T->knn_rec(0, q, k, heap);
+  for (int i = 0; i < k; ++i) { idx[i] = i < (int)heap.size() ? heap[i].second : -1; d2[i] = i < (int)heap.size() ? heap[i].first : 0.0; }
+}
+
+// symmetric 3x3 eigen-decomposition (cyclic Jacobi); eigenvalues ascending, eigenvectors in the columns of V
+static void eig3(double A[3][3], double w[3], double V[3][3]) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 50; ++sweep) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (A[p][q] == 0.0) continue;
+        const double th = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+        for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+        for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+      }
+  }
+  int o[3] = {0, 1, 2};
+  std::sort(o, o + 3, [&](int a, int b) { return A[a][a] < A[b][b]; });
+  double Vs[3][3];
+  for (int j = 0; j < 3; ++j) { w[j] = A[o[j]][o[j]]; for (int i = 0; i < 3; ++i) Vs[i][j] = V[i][o[j]]; }
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = Vs[i][j];
+}
+
+// Frame::recomputeNormals (frame.cpp:244-255) -> getNeighbours(i, k) (:208-242, the point itself included) ->
+// pointSetPCA (common.h:331-346): centroid, cov = sum (p - c)(p - c)^T (not divided by n), normal = eigenvector of the
+// smallest eigenvalue (SelfAdjointEigenSolver [ext-knowledge Eigen]: unit norm, sign arbitrary), flipped so that n.z <= 0.
+// nn_out (nullable): the k neighbour indices per point, in knnSearch order.
+void orc_recompute_normals(const double* pts, int64_t n, int k, double* nor_out, int32_t* nn_out, int num_threads) {
+  KdTree T(pts, n);
+#pragma omp parallel for num_threads(num_threads > 0 ? num_threads : 1) schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    std::vector<std::pair<double, int32_t>> heap;
+    T.knn_rec(0, pts + 3 * i, k, heap);
+    const int m = (int)heap.size();
+    double c[3] = {0, 0, 0};
+    for (int j = 0; j < m; ++j) for (int a = 0; a < 3; ++a) c[a] += pts[3 * (int64_t)heap[j].second + a];
+    for (int a = 0; a < 3; ++a) c[a] /= m;
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int j = 0; j < m; ++j) {
+      double d[3]; for (int a = 0; a < 3; ++a) d[a] = pts[3 * (int64_t)heap[j].second + a] - c[a];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[a][b] += d[a] * d[b];
+    }
+    double w[3], V[3][3]; eig3(C, w, V);
+    double nv[3] = {V[0][0], V[1][0], V[2][0]};
+    if (nv[2] > 0) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }   // "flip towards camera" common.h:343
+    for (int a = 0; a < 3; ++a) nor_out[3 * i + a] = nv[a];
+    if (nn_out) for (int j = 0; j < k; ++j) nn_out[(int64_t)k * i + j] = j < m ? heap[j].second : -1;
   }
 }
 

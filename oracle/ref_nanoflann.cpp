@@ -8,6 +8,7 @@
 // (git-ignored, travels to the GPU box).  Used (a) to pin oracle_icp.cpp's correspondence
 // restatement and (b) as the "reference" CPU baseline of the correspondence step in bench.py.
 #include <cstdint>
+#include <vector>
 #include <nanoflann.hpp>
 #ifdef _OPENMP
 #include <omp.h>
@@ -43,6 +44,12 @@ void ref_kd_query(void* h, const double* q, int64_t* idx, double* d2) {
   rs.init(&ret_index, &out);
   ((Index*)h)->tree->findNeighbors(rs, q, nanoflann::SearchParams(32, 0, false));
   *idx = (int64_t)ret_index; *d2 = out;
+}
+// Frame::getNeighbours' knnSearch (frame.cpp:208-225): k nearest to a query, ascending distance
+void ref_kd_knn(void* h, const double* q, int64_t k, int64_t* idx, double* d2) {
+  std::vector<size_t> ri(k); std::vector<double> rd(k);
+  ((Index*)h)->tree->knnSearch(q, (size_t)k, ri.data(), rd.data());
+  for (int64_t i = 0; i < k; ++i) { idx[i] = (int64_t)ri[i]; d2[i] = rd[i]; }
 }
 // all src points of one edge (frame.cpp:129-138), transform restated in geom.h / oracle_icp.cpp
 void ref_closest_points(void* h, const double* src_pts, int64_t n_src, const double* pose_src16,
