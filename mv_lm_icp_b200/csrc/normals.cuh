@@ -43,6 +43,7 @@ __device__ __forceinline__ void nn_exact(const FrameDev& fd, int64_t pos, const 
   if (pi == INT_MAX) return;   // padding
   const double d = d2_rn(s.qx, s.qy, s.qz, px, py, pz);
   if (s.count == s.k && !(d < s.bd[s.k - 1] || (d == s.bd[s.k - 1] && pi < s.bi[s.k - 1]))) return;
+  for (int j = 0; j < s.count; ++j) if (s.bi[j] == pi) return;   // a leaf can be reached twice (start leaf, then through the tree)
   int i = s.count < s.k ? s.count : s.k - 1;
   while (i > 0 && (s.bd[i - 1] > d || (s.bd[i - 1] == d && s.bi[i - 1] > pi))) { s.bd[i] = s.bd[i - 1]; s.bi[i] = s.bi[i - 1]; --i; }
   s.bd[i] = d; s.bi[i] = pi;
