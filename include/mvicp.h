@@ -147,6 +147,8 @@ int mvicp_pairwise(const mvicp_config* cfg, int32_t param, int32_t cost, const d
  * (N x 3 doubles) so that the caller can store them in Frame::nor. */
 int mvicp_recompute_normals(mvicp_ctx* ctx, int32_t k);
 int mvicp_get_normals(mvicp_ctx* ctx, int32_t frame, double* nor_xyz, float* elapsed_ms /*nullable: device time of the recompute*/);
+/* Frame::getNeighbours(i, k) for every point i of one frame (frame.cpp:208-242): nn_idx[i*k + j], ascending distance. */
+int mvicp_knn_self(mvicp_ctx* ctx, int32_t frame, int32_t k, int32_t* nn_idx);
 
 /* ---- multi-GPU: one process per GPU, frames sharded by owner = frame * world / n_frames ------------------ */
 int mvicp_nccl_unique_id(void* out128);   /* rank 0 creates, the launcher broadcasts the 128 bytes */

@@ -152,6 +152,12 @@ class Engine:
             out.append(nor)
         return out, ms.value
 
+    def knn_self(self, frame, k=10):
+        """Frame::getNeighbours for every point of a frame (frame.cpp:208-242): int32 [N, k]."""
+        nn = np.empty((self.n_pts[frame], k), np.int32)
+        check(self._l.mvicp_knn_self(self._ctx, C.c_int32(frame), C.c_int32(k), _p(nn, C.c_int32)))
+        return nn
+
     # ---- multi-GPU / introspection ---------------------------------------------------------------------
     def comm_init(self, unique_id, rank, world):
         check(self._l.mvicp_comm_init(self._ctx, C.c_char_p(unique_id), C.c_int32(rank), C.c_int32(world)))

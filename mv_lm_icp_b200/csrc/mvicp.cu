@@ -851,6 +851,23 @@ int mvicp_get_normals(mvicp_ctx* c, int32_t frame, double* nor_xyz, float* elaps
   return MVICP_OK;
 }
 
+// Frame::getNeighbours for every point of one frame (frame.cpp:208-242): the k nearest neighbours, knnSearch order.
+int mvicp_knn_self(mvicp_ctx* c, int32_t frame, int32_t k, int32_t* nn_idx) {
+  if (!c || frame < 0 || frame >= c->M || !nn_idx || k < 1 || k > KNN_MAXK) return fail(MVICP_ERR_INVALID, "mvicp_knn_self: bad arguments");
+  CU(cudaSetDevice(c->device));
+  const int n = (int)c->n_pts[frame];
+  double* d_nor = nullptr; int32_t* d_nn = nullptr;
+  CU(cudaMalloc(&d_nor, sizeof(double) * 3 * (size_t)n)); CU(cudaMalloc(&d_nn, sizeof(int32_t) * (size_t)k * n));
+  if (c->f32) normals_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), frame, k, d_nor, d_nn);
+  else normals_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), frame, k, d_nor, d_nn);
+  c->stats.kernel_launches += 1;
+  CU(cudaMemcpyAsync(nn_idx, d_nn, sizeof(int32_t) * (size_t)k * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_nor); cudaFree(d_nn);
+  CU(cudaGetLastError());
+  return MVICP_OK;
+}
+
 // ---- multi-GPU ---------------------------------------------------------------------------------------
 int mvicp_nccl_unique_id(void* out128) {
   if (!out128) return fail(MVICP_ERR_INVALID, "mvicp_nccl_unique_id: null");
