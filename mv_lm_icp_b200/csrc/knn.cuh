@@ -96,6 +96,7 @@ __device__ __forceinline__ float pt_d32(const float4& r, const Q& s) {
 template <bool F32, class Q>
 __device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int sub, Q& s) {
   const int64_t pos = (int64_t)leaf * LEAF + 2 * sub;
+  if (pos >= fd.n) return;   // padding leaf of the implicit tree (reachable only while the bound is still infinite)
   const float4 r0 = __ldg(fd.pts_sf + pos), r1 = __ldg(fd.pts_sf + pos + 1);
   const float d0 = pt_d32(r0, s), d1 = pt_d32(r1, s);
   if (d0 <= s.bound32) nn_exact<F32>(fd, pos, r0, s);
