@@ -71,3 +71,39 @@ def test_pose_graph_knn_is_the_ring(oracle):
     assert sorted(edges) == sorted(synth.ring_edges(6, 2))
     for i in range(6):
         assert set(nb[i].tolist()) == {(i - 1) % 6, (i + 1) % 6}
+
+
+def test_knn_restatement_equals_reference_nanoflann(oracle, golden_dir):
+    """Frame::getNeighbours (frame.cpp:208-242): the oracle's k-NN against the reference's nanoflann knnSearch on the
+    reference's own scan.  Squared distances must agree bit for bit; indices may differ only inside groups of exactly
+    equal distance (the scan's coordinates are quantised, so such ties exist; nanoflann orders them by traversal)."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    g = np.load(f"{golden_dir}/bunny_pair.npz")
+    pts = g["pts0"]
+    kd = oracle.KdIndex(pts, "kd"); rf = oracle.KdIndex(pts, "ref")
+    differing = 0
+    for i in range(0, len(pts), 53):
+        a = oracle.knn(kd, pts[i], 10); b = oracle.knn(rf, pts[i], 10)
+        assert np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
+        assert a[0][0] == i == b[0][0] and a[1][0] == 0.0            # the point itself comes first
+        if not np.array_equal(a[0], b[0]):
+            differing += 1
+            for j in np.where(a[0] != b[0])[0]:                      # every disagreement sits in a tie group
+                assert (a[1] == a[1][j]).sum() > 1 or np.sum((pts[b[0][j]] - pts[i]) ** 2) == a[1][-1]
+    assert differing > 0    # documents that ties do occur on the real scans
+
+
+def test_normals_restatement(oracle, golden_dir):
+    """pointSetPCA (common.h:331-346) restated: unit eigenvector of the smallest eigenvalue of sum (p-c)(p-c)^T over the
+    10 nearest neighbours, flipped to n.z <= 0 -- checked against numpy.linalg.eigh."""
+    sc = scene(3, 4000, 31)
+    pts = sc["pts"][1]
+    nor, nn = oracle.recompute_normals(pts, 10, threads=4, want_nn=True)
+    assert np.all(nor[:, 2] <= 0) and np.max(np.abs(np.linalg.norm(nor, axis=1) - 1)) < 1e-12
+    P = pts[nn]; C = P - P.mean(1, keepdims=True)
+    w, V = np.linalg.eigh(np.einsum("nki,nkj->nij", C, C))
+    v = V[:, :, 0]; v = np.where(v[:, 2:3] > 0, -v, v)
+    good = (w[:, 1] - w[:, 0]) > 1e-6 * w[:, 2]
+    assert good.mean() > 0.99 and np.max(np.abs(v[good] - nor[good])) < 1e-7
+    assert np.median(np.abs(np.sum(nor * sc["nor"][1], axis=1))) > 0.99     # and they are the surface normals
