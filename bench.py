@@ -100,6 +100,15 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -285,9 +294,11 @@ def run_ours(args, cfg):
                  "lm_eval": lm_eval_ms / dev_ms, "lm_other": sum(p["lm_other_ms"] for p in per) / dev_ms}
         dominant = "knn" if share["knn"] >= share["lm_eval"] else "lm_eval"
         roof_knn = {"kernel": "knn_kernel", "bound": "hbm", "achieved": knn_gbs, "peak": peak, "unit": "GB/s", "frac": knn_gbs / peak,
-                    "traffic": None, "algorithmic_bytes_per_launch": knn_bytes, "avg_launch_ms": knn_ms, "peak_source": peak_src}
+                    "traffic": measured_traffic("knn_kernel") if world == 1 else None, "algorithmic_bytes_per_launch": knn_bytes,
+                    "avg_launch_ms": knn_ms, "peak_source": peak_src}
         roof_lm = {"kernel": "lm_eval_kernel", "bound": "hbm", "achieved": lm_gbs, "peak": peak, "unit": "GB/s", "frac": lm_gbs / peak,
-                   "traffic": None, "algorithmic_bytes_per_launch": lm_bytes, "avg_launch_ms": lm_eval_ms / max(1, evals), "peak_source": peak_src}
+                   "traffic": measured_traffic("lm_eval_kernel") if world == 1 else None, "algorithmic_bytes_per_launch": lm_bytes,
+                   "avg_launch_ms": lm_eval_ms / max(1, evals), "peak_source": peak_src}
         pose_bytes = M * 16 * 8
         out = {"metric": "ICP iterations/sec (corr+LM)", "value": 1e3 / ms_per_step, "unit": "iter/s", "n_gpus": world, "steps": K,
                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -18,7 +18,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _run(rank, world, port, out_dir):
+def _run(rank, world, port, out_dir, flags):
     import torch.distributed as dist
     import mv_lm_icp_b200 as mv
     from mv_lm_icp_b200.dist import broadcast_unique_id
@@ -27,7 +27,7 @@ def _run(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     sc = scene(6, 20011, 22)
     edges = synth.ring_edges(6, 2)
-    eng = mv.Engine(device=rank)
+    eng = mv.Engine(device=rank, flags=flags)
     eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges)
     eng.comm_init(broadcast_unique_id(mv.nccl_unique_id, rank, device="cuda"), rank, world)
     eng.set_poses(sc["poses_init"])
@@ -42,7 +42,8 @@ def _run(rank, world, port, out_dir):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpus_bit_identical_to_one(tmp_path):
+@pytest.mark.parametrize("flags", [0, 2], ids=["peer-memory", "nccl-only"])
+def test_two_gpus_bit_identical_to_one(tmp_path, flags):
     import mv_lm_icp_b200 as mv
     sc = scene(6, 20011, 22)
     edges = synth.ring_edges(6, 2)
@@ -52,7 +53,7 @@ def test_two_gpus_bit_identical_to_one(tmp_path):
         s = eng.icp_round(0.05, mv.PARAM_SE3, mv.COST_P2PLANE, True)
         ref.append((eng.get_poses(), s["num_iterations"]))
     eng.close()
-    mp.spawn(_run, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_run, args=(2, _free_port(), str(tmp_path), flags), nprocs=2, join=True)
     for r in range(2):
         P = np.load(tmp_path / f"poses_{r}.npy"); it = np.load(tmp_path / f"iters_{r}.npy")
         assert it.tolist() == [x[1] for x in ref]
