@@ -744,9 +744,10 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     ++seen;
     if (fin || seen > max_evals) break;
   }
-  // sharded runs: every rank holds identical poses (identical solve on identical all-reduced blocks); the
-  // owners' copies are gathered anyway so that a caller never sees rank-dependent state.
-  if (c->comm && c->world > 1) {
+  // sharded runs: every rank holds bit-identical poses (the same lm_step_kernel ran on bit-identical pair matrices), so
+  // no pose exchange is needed; the NCCL-only mode still all-gathers the owners' copies (6-dof poses per outer iteration,
+  // as the north-star words it) -- it costs ~0.1 ms of small copies at 8 ranks and changes nothing.
+  if (c->comm && c->world > 1 && !use_p2p) {
     const int chunk = (M + c->world - 1) / c->world;
     RET(c->d_posegather.reserve(sizeof(double) * 16 * (size_t)chunk * c->world * 2));
     double* sendb = c->d_posegather.as<double>();
