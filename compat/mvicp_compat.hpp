@@ -29,12 +29,13 @@ struct Session {
   mvicp_ctx* ctx = nullptr;
   const std::vector<std::shared_ptr<FrameT>>* frames = nullptr;
   std::vector<int32_t> e_src, e_dst;
-  bool corr_valid = false;
+  bool corr_valid = false, graph_pushed = false;
   ~Session() { mvicp_destroy(ctx); }
 
   void bind(const std::vector<std::shared_ptr<FrameT>>& fr) {
     if (ctx && frames == &fr) return;
     if (ctx) { mvicp_destroy(ctx); ctx = nullptr; }
+    graph_pushed = false;
     mvicp_config cfg{0, 0, nullptr};
     check(mvicp_create(&cfg, &ctx));
     frames = &fr;
@@ -53,10 +54,13 @@ struct Session {
     for (size_t i = 0; i < frames->size(); ++i) std::copy(P.begin() + 16 * i, P.begin() + 16 * (i + 1), (*frames)[i]->pose.data());
   }
   void push_graph() {   // Frame::neighbours[*].neighbourIdx, in the reference's iteration order
-    e_src.clear(); e_dst.clear();
+    std::vector<int32_t> ns, nd;
     for (size_t i = 0; i < frames->size(); ++i)
-      for (auto& ne : (*frames)[i]->neighbours) { e_src.push_back((int32_t)i); e_dst.push_back(ne.neighbourIdx); }
+      for (auto& ne : (*frames)[i]->neighbours) { ns.push_back((int32_t)i); nd.push_back(ne.neighbourIdx); }
+    if (graph_pushed && ns == e_src && nd == e_dst) return;   // unchanged: keep the engine's per-edge search seeds
+    e_src.swap(ns); e_dst.swap(nd);
     check(mvicp_set_graph(ctx, (int32_t)e_src.size(), e_src.data(), e_dst.data()));
+    graph_pushed = true;
   }
 };
 
