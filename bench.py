@@ -200,7 +200,7 @@ def run_ours(args, cfg):
     param, cost = PARAM[cfg["param"]], COST[cfg["cost"]]
 
     t_setup0 = time.perf_counter()
-    eng = mv.Engine(device=dev)
+    eng = mv.Engine(device=dev, flags=args.flags)
     eng.set_frames(sc["pts"], sc["nor"])
     eng.set_graph(edges)
     if world > 1:
@@ -346,6 +346,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--flags", type=int, default=0, help="MVICP_FLAG_* bits for the engine (A/B measurements)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

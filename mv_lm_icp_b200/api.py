@@ -15,6 +15,8 @@ COST_P2P, COST_P2PLANE, COST_MIXED = 0, 1, 2
 TERMINATION = ["FUNCTION_TOLERANCE", "GRADIENT_TOLERANCE", "PARAMETER_TOLERANCE", "MAX_ITERATIONS", "MIN_RADIUS",
                "INVALID_STEPS", "EVAL_FAILURE"]
 FLAG_NO_SEED = 1
+FLAG_NCCL_ONLY = 2
+FLAG_WARP_SEARCH = 4
 
 
 def _p(a, t=C.c_double):

@@ -407,10 +407,12 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
-  if (c->n_knn_tiles)
-    knn_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
+  if (c->n_knn_tiles) {
+    auto kern = (c->flags & MVICP_FLAG_WARP_SEARCH) ? knn_kernel<F32, true> : knn_kernel<F32, false>;
+    kern<<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
         c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
         c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh);
+  }
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);
   // exact median -> weight

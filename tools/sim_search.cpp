@@ -15,7 +15,13 @@ static inline float lb32(const Box& b, float fx, float fy, float fz) {
 }
 
 extern "C" {
+static unsigned char* g_trace = nullptr; static int g_trace_cap = 0, g_trace_n = 0;
+extern "C" void sim_set_trace(unsigned char* t, int cap) { g_trace = t; g_trace_cap = cap; }
+extern "C" int sim_trace_len() { return g_trace_n; }
+static double g_cap = INFINITY; static int g_coarse = 0;
+extern "C" void sim_set_coarse(int c) { g_coarse = c; }
 void sim_config(int, double) {}
+void sim_set_cap(double c) { g_cap = c; }
 void* sim_build(const double* pts, int64_t n) {
   Sim* s = new Sim(); s->n = n; s->pts = pts;
   build_frame(pts, n, s->b);
@@ -25,13 +31,15 @@ void* sim_build(const double* pts, int64_t n) {
   return s;
 }
 void sim_free(void* h) { delete (Sim*)h; }
+void sim_order(void* h, int* out) { Sim& s = *(Sim*)h; for (int64_t i = 0; i < s.n; ++i) out[i] = s.b.order[i]; }
 int sim_leaf_of(void* h, int orig) { return ((Sim*)h)->b.pos_of[orig] / LEAF; }
 // returns NN original index; counts[0] = box tests, counts[1] = point tests, counts[2] = loop steps
 int sim_query(void* h, const double* q, int start_leaf, int reseed, int64_t* counts) {
   Sim& s = *(Sim*)h; const HostFrameBuild& t = s.b; const int L = t.n_leaf_pad;
   const float fx = (float)q[0], fy = (float)q[1], fz = (float)q[2];
-  float bound = INFINITY; double best = INFINITY; int bi = INT32_MAX;
-  int64_t nb = 0, np = 0, ns = 0;
+  double best = g_cap; int bi = INT32_MAX; float bound = std::isinf(g_cap) ? INFINITY : (float)((std::sqrt(best) + 1e-6) * (std::sqrt(best) + 1e-6) * 1.000001);
+  int64_t nb = 0, np = 0, ns = 0; g_trace_n = 0;
+  auto tr = [&](unsigned char c) { if (g_trace && g_trace_n < g_trace_cap) g_trace[g_trace_n++] = c; };
   auto scan2 = [&](int leaf, int sub) {
     for (int j = 0; j < 2; ++j) {
       const int64_t pos = (int64_t)leaf * LEAF + 2 * sub + j; ++np;
@@ -44,22 +52,24 @@ int sim_query(void* h, const double* q, int start_leaf, int reseed, int64_t* cou
       }
     }
   };
-  int leaf_node = -1;
+  int leaf_node = -1; bool coarse_on = false;
   if (start_leaf >= 0) {
     leaf_node = L + start_leaf;
-    for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(start_leaf, sub); ++ns; }
+    for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(start_leaf, sub); ++ns; tr(3); }
     const Box& b = t.boxes[leaf_node];
     const float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
     if (reseed && bound > 16.f * (ex * ex + ey * ey + ez * ez)) start_leaf = -1;
   }
   if (start_leaf < 0) {
     int node = 1;
-    while (node < L) { const float l0 = lb32(t.boxes[2 * node], fx, fy, fz), l1 = lb32(t.boxes[2 * node + 1], fx, fy, fz); nb += 2; ++ns; node = (l1 < l0) ? 2 * node + 1 : 2 * node; }
-    if (node != leaf_node) for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(node - L, sub); ++ns; }
+    while (node < (L >> g_coarse)) { const float l0 = lb32(t.boxes[2 * node], fx, fy, fz), l1 = lb32(t.boxes[2 * node + 1], fx, fy, fz); nb += 2; ++ns; tr(4); node = (l1 < l0) ? 2 * node + 1 : 2 * node; }
+    if (g_coarse) { const int first = (node << g_coarse) - L; for (int lf = first; lf < first + (1 << g_coarse); ++lf) for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(lf, sub); ++ns; } coarse_on = true; }
+    else if (node != leaf_node) for (int sub = 0; sub < LEAF / 2; ++sub) { scan2(node - L, sub); ++ns; tr(5); }
     leaf_node = node;
   }
   std::vector<int> sn; std::vector<float> sl;
-  for (int l = t.depth - 1; l >= 0; --l) {
+  const int cz = coarse_on ? g_coarse : 0; const int Lc = L >> cz;
+  for (int l = t.depth - 1 - cz; l >= 0; --l) {
     const int sib = (leaf_node >> l) ^ 1;
     const float face = t.faces[sib]; uint32_t bits; std::memcpy(&bits, &face, 4); const int axis = bits & 3;
     const float qa = axis == 0 ? fx : (axis == 1 ? fy : fz);
@@ -70,8 +80,8 @@ int sim_query(void* h, const double* q, int start_leaf, int reseed, int64_t* cou
   int node = -1, sub = 0;
   while (true) {
     if (node < 0) { if (sn.empty()) break; const int nn = sn.back(); const float ll = sl.back(); sn.pop_back(); sl.pop_back(); if (ll > bound) continue; node = nn; sub = 0; }
-    ++ns;
-    if (node >= L) { scan2(node - L, sub); if (++sub == LEAF / 2) node = -1; }
+    ++ns; tr(node >= Lc ? 2 : 1);
+    if (node >= Lc) { const int first = (node << cz) - L; scan2(first + sub / (LEAF / 2), sub % (LEAF / 2)); if (++sub == (LEAF / 2) << cz) node = -1; }
     else {
       const int c0 = 2 * node; const float l0 = lb32(t.boxes[c0], fx, fy, fz), l1 = lb32(t.boxes[c0 + 1], fx, fy, fz); nb += 2;
       const bool f0 = l0 <= l1; const float ln = f0 ? l0 : l1, lf = f0 ? l1 : l0;
