@@ -92,46 +92,121 @@ __global__ void lm_init_kernel(LmWork w) {
 }
 
 // ---- dense Cholesky solve --------------------------------------------------------------------------------------
-// L: (n+1) rows of stride ld; rows 0..n-1 hold the lower triangle of the SPD matrix, row n holds the right-hand side.
-// Right-looking factorisation; treating the rhs as an extra row performs the forward substitution for free.  Each
-// scaled column is stashed contiguously (colj) so the rank-1 update reads conflict-free; the diagonal of the factor
-// goes to dg.  The back substitution runs in one warp (shuffle-free, __syncwarp only).  Solution returned in y[0..n).
-__device__ bool chol_solve(double* L, int ld, int n, double* colj, double* dg, double* y, const int32_t* __restrict__ rlast,
+// L: (n+1) rows of stride ld; rows 0..n-1 hold the lower triangle of the SPD matrix, row n holds the right-hand side
+// (treating the rhs as an extra row performs the forward substitution for free).  n is a multiple of 6 (one 6x6 block
+// per free pose), and the factorisation is right-looking over those blocks -- 2 barriers per pose instead of 2 per
+// column, which is what the single-CTA solve is bound by:
+//   (a) every thread factors the 6x6 diagonal block redundantly in registers (no communication),
+//   (b) panel: one thread per row below it solves its 6 entries against that block,
+//   (c) trailing update: one warp per row, lanes over columns, 6 multiply-adds per entry.
+// Rows whose profile starts right of the block (rfirst) and rows beyond rlast are structurally zero in the block
+// (envelope of the block-sparse normal matrix; fill-in stays inside each row's profile) and are skipped: only entries
+// inside the row profiles [rfirst[r], r] are ever read or written, the rest of L may hold anything.
+// scratch: >= 2n ints (row profiles staged in shared memory); dinv: reciprocal diagonal of the factor.
+// The back substitution runs block-wise in one warp.  Solution returned in y[0..n).
+__device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* dinv, double* y, const int32_t* __restrict__ rlast,
                            const int32_t* __restrict__ rfirst) {
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
-  for (int j = 0; j < n; ++j) {
+  int32_t* s_rfirst = reinterpret_cast<int32_t*>(scratch);
+  int32_t* s_rlast = s_rfirst + n;
+  for (int i = tid; i < n; i += T) { s_rfirst[i] = rfirst[i]; s_rlast[i] = rlast[i]; }
+  const int NB = n / 6;
+  for (int J = 0; J < NB; ++J) {
+    const int j0 = 6 * J;
     __syncthreads();
-    const double d = L[(size_t)j * ld + j];
-    if (!(d > 0.0) || !isfinite(d)) return false;     // uniform: every thread reads the same value
-    const double sd = sqrt(d), inv = 1.0 / sd;
-    // rows beyond rlast[j] are structurally zero in column j (envelope of the block-sparse matrix: the factor fills
-    // only inside each row's profile), so the rank-1 update is confined to rows/cols (j, rlast[j]] plus the rhs row n
-    const int rl = rlast[j];
-    for (int r = j + tid; r <= rl; r += T) {
-      if (r == j) { colj[j] = sd; dg[j] = sd; }
-      else { const double v = L[(size_t)r * ld + j] * inv; L[(size_t)r * ld + j] = v; colj[r] = v; }
+    // (a) 6x6 diagonal block, lower triangle D[i][k] (k <= i), factored in place; every thread gets the same values
+    double D[6][6], inv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int k = 0; k <= i; ++k) D[i][k] = L[(size_t)(j0 + i) * ld + j0 + k];
+    bool okb = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double d = D[k][k];
+#pragma unroll
+      for (int m = 0; m < k; ++m) d -= D[k][m] * D[k][m];
+      if (!(d > 0.0) || !isfinite(d)) okb = false;
+      const double sd = sqrt(d);
+      inv[k] = 1.0 / sd; D[k][k] = sd;
+#pragma unroll
+      for (int i = k + 1; i < 6; ++i) {
+        double v = D[i][k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) v -= D[i][m] * D[k][m];
+        D[i][k] = v * inv[k];
+      }
     }
-    if (tid == 0) { const double v = L[(size_t)n * ld + j] * inv; L[(size_t)n * ld + j] = v; colj[n] = v; }
+    if (!okb) return false;                       // uniform: every thread computed the same block
+    const int rl = s_rlast[j0 + 5];
+    const int nrows = rl - (j0 + 5) + 1;          // rows j0+6..rl and the rhs row
+    // (b) panel: L[r][j0..j0+5] <- A[r][j0..j0+5] * L_JJ^-T
+    for (int q = tid; q < nrows; q += T) {
+      const int r = (q == nrows - 1) ? n : j0 + 6 + q;
+      if (r < n && s_rfirst[r] > j0 + 5) continue;
+      double* row = L + (size_t)r * ld + j0;
+      double v[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double a = row[k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) a -= v[m] * D[k][m];
+        v[k] = a * inv[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) row[k] = v[k];
+    }
     __syncthreads();
-    const int nrows = rl - j + 1;   // rows j+1..rl and the rhs row
+    if (tid == T - 1) {                            // everybody has read the diagonal block by now: store its factor
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int k = 0; k <= i; ++k) L[(size_t)(j0 + i) * ld + j0 + k] = D[i][k];
+        dinv[j0 + i] = inv[i];
+      }
+    }
+    // (c) trailing update: A[r][c] -= sum_k L[r][j0+k] L[c][j0+k] for j0+5 < c <= min(r, rl)
     for (int q = wid; q < nrows; q += nw) {
-      const int r = (q == nrows - 1) ? n : j + 1 + q;
-      const double lr = colj[r];
+      const int r = (q == nrows - 1) ? n : j0 + 6 + q;
+      if (r < n && s_rfirst[r] > j0 + 5) continue;
       double* row = L + (size_t)r * ld;
+      double lr[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) lr[k] = row[j0 + k];
       const int cend = min(r, rl);
-      for (int c = j + 1 + lane; c <= cend; c += 32) row[c] -= lr * colj[c];
+      for (int c = j0 + 6 + lane; c <= cend; c += 32) {
+        if (s_rfirst[c] > j0 + 5) continue;        // row c has nothing in this block: contributes exactly zero
+        const double* lc = L + (size_t)c * ld + j0;
+        double a = row[c];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a -= lr[k] * lc[k];
+        row[c] = a;
+      }
     }
   }
   __syncthreads();
   for (int i = tid; i < n; i += T) y[i] = L[(size_t)n * ld + i];   // forward-substituted rhs
   __syncthreads();
   if (wid == 0) {
-    for (int j = n - 1; j >= 0; --j) {     // L^T x = z
-      const double yj = y[j] / dg[j];
+    for (int J = NB - 1; J >= 0; --J) {     // L^T x = z, one pose block at a time
+      const int j0 = 6 * J;
+      double x[6];
+#pragma unroll
+      for (int k = 5; k >= 0; --k) {
+        double a = y[j0 + k];
+#pragma unroll
+        for (int m = k + 1; m < 6; ++m) a -= L[(size_t)(j0 + m) * ld + j0 + k] * x[m];
+        x[k] = a * dinv[j0 + k];
+      }
       __syncwarp();
-      if (lane == 0) y[j] = yj;
-      const double* row = L + (size_t)j * ld;
-      for (int i = rfirst[j] + lane; i < j; i += 32) y[i] -= row[i] * yj;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (lane == k) y[j0 + k] = x[k];
+      for (int i = s_rfirst[j0] + lane; i < j0; i += 32) {
+        double a = y[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a -= L[(size_t)(j0 + k) * ld + i] * x[k];
+        y[i] = a;
+      }
       __syncwarp();
     }
   }
@@ -143,9 +218,15 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   extern __shared__ double smem[];
   __shared__ double red[40];
   __shared__ int s_flag;
-  LmState* S = w.S;
-  if (S->done) { if (threadIdx.x == 0) { w.host_flag[w.seq & 7] = (w.seq << 1) | 1; __threadfence_system(); } return; }
+  if (w.S->done) { if (threadIdx.x == 0) { w.host_flag[w.seq & 7] = (w.seq << 1) | 1; __threadfence_system(); } return; }
   const int tid = threadIdx.x, T = blockDim.x;
+  // the state machine works on a shared-memory copy of LmState (dozens of dependent scalar reads per step) and writes it
+  // back once at the end; nobody else touches it while this kernel runs
+  __shared__ LmState s_state;
+  for (int i = tid; i < (int)(sizeof(LmState) / sizeof(int32_t)); i += T)
+    reinterpret_cast<int32_t*>(&s_state)[i] = reinterpret_cast<const int32_t*>(w.S)[i];
+  __syncthreads();
+  LmState* S = &s_state;
   const int n = S->n, M = S->M, E = S->E, param = S->param;
   if (w.peer_flags) {   // wait until every rank's edge kernel has delivered this iteration's pair matrices
     if (tid < w.world) {
@@ -161,8 +242,7 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   double* L = w.l_in_smem ? smem + 2 * (S->n + 1) : w.Lg;
 
   // ================= 1. gather the per-edge pair matrices (lm_edge_kernel) into Hc, gc; total cost ===================
-  for (int idx = tid; idx < n * n; idx += T) w.Hc[idx] = 0.0;
-  __syncthreads();
+  // (entries outside the listed blocks are zeroed once by the host when the block structure is built and never written)
   for (int idx = tid; idx < w.n_hblocks * 36; idx += T) {   // gather into the dense matrix, fixed order
     const int b = idx / 36, r = idx - 36 * b, i = r / 6, j = r - 6 * i;
     double s = 0;
@@ -222,7 +302,11 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   __syncthreads();
   take = s_flag != 0;
   if (take) {
-    for (int idx = tid; idx < n * n; idx += T) w.H[idx] = w.Hc[idx];
+    for (int idx = tid; idx < w.n_hblocks * 36; idx += T) {
+      const int b = idx / 36, r = idx - 36 * b, i = r / 6, j = r - 6 * i;
+      const size_t at = (size_t)(w.hb_row[b] + i) * n + w.hb_col[b] + j;
+      w.H[at] = w.Hc[at];
+    }
     for (int idx = tid; idx < n; idx += T) w.g[idx] = w.gc[idx];
     for (int idx = tid; idx < M * 7; idx += T) w.x[idx] = w.cand[idx];
     __syncthreads();
@@ -268,12 +352,13 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
       }
     __syncthreads();
     const int ldl = n | 1;   // odd stride: conflict-free column walks
-    for (int idx = tid; idx < n * n; idx += T) {
-      const int i = idx / n, j = idx - i * n;
-      if (j > i) continue;
-      double v = w.scale[i] * w.H[idx] * w.scale[j];
-      if (i == j) { const double ldg = sqrt(w.diag[i] / radius); v += ldg * ldg; }
-      L[(size_t)i * ldl + j] = v;
+    for (int i = tid >> 5; i < n; i += T >> 5) {          // one warp per row, only the row's profile (see chol_solve)
+      const double si = w.scale[i];
+      for (int j = w.rfirst[i] + (tid & 31); j <= i; j += 32) {
+        double v = si * w.H[(size_t)i * n + j] * w.scale[j];
+        if (i == j) { const double ldg = sqrt(w.diag[i] / radius); v += ldg * ldg; }
+        L[(size_t)i * ldl + j] = v;
+      }
     }
     for (int j = tid; j < n; j += T) L[(size_t)n * ldl + j] = w.scale[j] * w.g[j];
     __syncthreads();
@@ -339,7 +424,10 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     }
   }
   __syncthreads();
-  if (tid == 0) { w.host_flag[w.seq & 7] = (w.seq << 1) | (S->done ? 1 : 0); __threadfence_system(); }
+  for (int i = tid; i < (int)(sizeof(LmState) / sizeof(int32_t)); i += T)
+    reinterpret_cast<int32_t*>(w.S)[i] = reinterpret_cast<const int32_t*>(&s_state)[i];
+  __syncthreads();
+  if (tid == 0) { __threadfence(); w.host_flag[w.seq & 7] = (w.seq << 1) | (S->done ? 1 : 0); __threadfence_system(); }
 }
 
 }  // namespace mv

@@ -647,6 +647,9 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     RET(up(c->d_hc_sub, hc_sub)); RET(up(c->d_gb_ptr, gb_ptr)); RET(up(c->d_gc_edge, gc_edge)); RET(up(c->d_gc_side, gc_side));
     RET(up(c->d_col, c->h_col));
     RET(up(c->d_rlast, rlast)); RET(up(c->d_rfirst, rfirst));
+    // the step kernel writes only the listed blocks of the dense normal matrix; everything else stays zero from here
+    CU(cudaMemsetAsync(c->d_H.p, 0, sizeof(double) * (size_t)n * n, c->stream));
+    CU(cudaMemsetAsync(c->d_Hc.p, 0, sizeof(double) * (size_t)n * n, c->stream));
 
     CU(cudaStreamSynchronize(c->stream));   // the host vectors above must outlive their copies
     c->lm_key = key;
