@@ -277,6 +277,12 @@ def run_ours(args, cfg):
         import torch.distributed as dist
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms, e2e_ms = [float(x) for x in tot.cpu()]
+    mine = {k: round(sum(p[k] for p in per) / args.steps, 4) for k in ("knn_ms", "select_ms", "lm_eval_ms", "lm_other_ms")}
+    mine["queries"] = int(per[0]["queries"])
+    per_rank = [mine]
+    if world > 1:   # lm_other of a rank includes its wait for the slowest rank's matrices: the imbalance shows here
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     if rank == 0:
         peak, peak_src = hbm_peak()
         K = args.steps
@@ -307,12 +313,13 @@ def run_ours(args, cfg):
                           if args.config == 3 else f"config {args.config}: {M} views x {N} pts, {cfg['param']}, {cfg['cost']}",
                           "l2": "no flush: resident working set (clouds + trees + match arrays) = %.0f MB > 126 MB L2" %
                                 ((M * N * 48 + len(edges) * N * 12) / 1e6),
-                          "parallelism": f"frames sharded over {world} GPU(s), one process per GPU",
+                          "parallelism": f"edges (frame -> neighbour query sets) sharded over {world} GPU(s) by query count, one process per GPU",
                           "timing": "wall clock between barriers (host-driven LM loop); device-event sum = %.3f ms/step" % (dev_ms / K),
                           "setup_ms_excluded": setup_s * 1e3,
                           "normals_ms_excluded": normals_ms,
                           "lm_iterations_per_round": [p["lm_iters"] for p in per],
                           "per_round_ms": [round(p["ms"], 3) for p in per],
+                          "per_rank_ms_per_step": per_rank,
                           "storage": "fp32 records (lossless), fp64 arithmetic"},
                "e2e": {"value": 1e3 / (e2e_ms / K), "unit": "iter/s", "h2d_bytes_per_step": pose_bytes, "d2h_bytes_per_step": pose_bytes,
                        "note": "per step: poses host->device, correspond+optimize, poses device->host through the C ABI; clouds uploaded once "

@@ -11,7 +11,7 @@
  *   correspondence   : (int32 first = src index, int32 second = dst index, double dist)
  *   edge weight      : float (OutgoingEdge::weight)
  * Threading: one context = one host thread at a time (the reference is single-threaded).
- * One process per GPU; multi-GPU runs shard frames across processes (mvicp_comm_init).
+ * One process per GPU; multi-GPU runs shard the edges (frame -> neighbour query sets) across processes (mvicp_comm_init).
  */
 #ifndef MVICP_H
 #define MVICP_H
@@ -151,7 +151,8 @@ int mvicp_get_normals(mvicp_ctx* ctx, int32_t frame, double* nor_xyz, float* ela
 /* Frame::getNeighbours(i, k) for every point i of one frame (frame.cpp:208-242): nn_idx[i*k + j], ascending distance. */
 int mvicp_knn_self(mvicp_ctx* ctx, int32_t frame, int32_t k, int32_t* nn_idx);
 
-/* ---- multi-GPU: one process per GPU, frames sharded by owner = frame * world / n_frames ------------------ */
+/* ---- multi-GPU: one process per GPU; the edges with a free src frame, in graph order, are cut into world_size
+ * contiguous runs of equal query count (every rank holds all clouds and ends every call with identical poses) ---- */
 int mvicp_nccl_unique_id(void* out128);   /* rank 0 creates, the launcher broadcasts the 128 bytes */
 int mvicp_comm_init(mvicp_ctx* ctx, const void* id128, int32_t rank, int32_t world_size);
 

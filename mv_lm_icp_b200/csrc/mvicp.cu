@@ -81,6 +81,7 @@ struct mvicp_ctx {
   // graph
   int E = 0;
   std::vector<EdgeDev> h_edges;
+  std::vector<int32_t> edge_owner;   // rank that processes edge e (-1: src frame fixed, nobody)
   DevBuf d_edges, d_xf, d_corr, d_d2, d_count, d_sel, d_hist, d_weight, d_median, d_selcand, d_selcand_n;
   DevBuf d_knn_tiles, d_eval_tiles, d_edge_tile_begin, d_partial, d_blocks;
   int n_knn_tiles = 0, n_eval_tiles = 0, eval_tile_len = EVAL_TILE;
@@ -106,6 +107,24 @@ struct mvicp_ctx {
 };
 
 static inline int owner_of(const mvicp_ctx* c, int frame) { return (int)(((int64_t)frame * c->world) / std::max(1, c->M)); }
+// Sharding rule (mirrored in mv_lm_icp_b200/dist.py:edge_owners): the edges whose src frame is not fixed, in graph order,
+// are cut into `world` contiguous runs of (nearly) equal query count -- an edge goes to the rank that the midpoint of its
+// query range falls to.  Contiguous runs keep a rank on few src frames; cutting by queries rather than by frames keeps the
+// ranks within one edge of each other (20 frames over 8 ranks would be 3 frames against 2).
+static void assign_edge_owners(mvicp_ctx* c) {
+  const int E = c->E;
+  c->edge_owner.assign(E, -1);
+  int64_t total = 0;
+  for (int e = 0; e < E; ++e) if (!c->fixed[c->h_edges[e].src]) total += c->n_pts[c->h_edges[e].src];
+  int64_t before = 0;
+  for (int e = 0; e < E; ++e) {
+    const int s = c->h_edges[e].src;
+    if (c->fixed[s]) continue;
+    const int64_t n = c->n_pts[s];
+    c->edge_owner[e] = total > 0 ? (int)std::min<int64_t>(c->world - 1, ((2 * before + n) * c->world) / (2 * total)) : 0;
+    before += n;
+  }
+}
 
 // =================================================================================================
 // one-time per-frame search structure (replaces the lazily built nanoflann index, frame.cpp:188-193)
@@ -311,10 +330,11 @@ static int rebuild_work(mvicp_ctx* c) {
   const int E = c->E;
   if (!E) return MVICP_OK;
   int64_t off = 0, owned_slots = 0;
+  assign_edge_owners(c);
   for (int e = 0; e < E; ++e) {
     EdgeDev& ed = c->h_edges[e];
     ed.off = off; ed.n_src = (int32_t)c->n_pts[ed.src];
-    ed.owned = (owner_of(c, ed.src) == c->rank && !c->fixed[ed.src]) ? 1 : 0;   // fixed src: `if(this->fixed) return;` frame.cpp:93
+    ed.owned = c->edge_owner[e] == c->rank ? 1 : 0;   // fixed src: nobody (`if(this->fixed) return;` frame.cpp:93)
     off += ed.n_src;
     if (ed.owned) owned_slots += ed.n_src;
   }
@@ -464,7 +484,7 @@ int mvicp_get_edge(mvicp_ctx* c, int32_t e, int32_t* first, int32_t* second, dou
   if (!c || e < 0 || e >= c->E) return fail(MVICP_ERR_INVALID, "mvicp_get_edge: bad edge");
   CU(cudaSetDevice(c->device));
   const EdgeDev& ed = c->h_edges[e];
-  if (!ed.owned && !c->fixed[ed.src]) return fail(MVICP_ERR_NOT_OWNER, "edge %d is processed by rank %d", e, owner_of(c, ed.src));
+  if (!ed.owned && !c->fixed[ed.src]) return fail(MVICP_ERR_NOT_OWNER, "edge %d is processed by rank %d", e, c->edge_owner[e]);
   RET(fetch_edge_meta(c));
   if (weight) *weight = c->h_weight[e];
   if (count) *count = (int64_t)c->h_count[e];
@@ -599,8 +619,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   // ownership may depend on `fixed`: refresh the edge table if it changed
   bool stale = false;
   for (int e = 0; e < E; ++e) {
-    const int want = (owner_of(c, c->h_edges[e].src) == c->rank && !c->fixed[c->h_edges[e].src]) ? 1 : 0;
-    if (want != c->h_edges[e].owned) stale = true;
+    if ((c->edge_owner[e] < 0) != (c->fixed[c->h_edges[e].src] != 0)) stale = true;
   }
   if (stale) return fail(MVICP_ERR_STATE, "fixed flags changed after mvicp_set_graph: call mvicp_set_graph again");
   // the gather lists / envelope depend only on the graph and the fixed flags: build and upload them when those change

@@ -1,23 +1,27 @@
 """Host-side sharding rules of the multi-GPU path (one process per GPU), mirrored from csrc/mvicp.cu so that they
-can be tested on CPU with gloo: frame ownership, edge ownership, and the zero-padded all-reduce that acts as an
+can be tested on CPU with gloo: edge ownership (balanced by query count), and the zero-padded all-reduce that acts as an
 order-independent all-gather of per-edge blocks."""
 import numpy as np
 
 
-def frame_owner(frame, world, n_frames):
-    """owner = frame * world / n_frames (block distribution; csrc/mvicp.cu owner_of)."""
-    return (frame * world) // max(1, n_frames)
-
-
-def owned_edges(edges, rank, world, n_frames, fixed=None):
-    """Edges processed by `rank`: those whose src frame it owns and whose src is not fixed (frame.cpp:93)."""
-    out = []
-    for e, (s, d) in enumerate(edges):
-        if fixed is not None and fixed[s]:
-            continue
-        if frame_owner(s, world, n_frames) == rank:
-            out.append(e)
+def edge_owners(edges, n_pts, world, fixed=None):
+    """Rank that processes each edge (-1: src frame fixed, nobody) -- csrc/mvicp.cu assign_edge_owners: the edges whose
+    src is not fixed, in graph order, are cut into `world` contiguous runs of (nearly) equal query count; an edge goes to
+    the rank that the midpoint of its query range falls to."""
+    act = [e for e, (s, d) in enumerate(edges) if fixed is None or not fixed[s]]
+    total = sum(int(n_pts[edges[e][0]]) for e in act)
+    out = [-1] * len(edges)
+    before = 0
+    for e in act:
+        n = int(n_pts[edges[e][0]])
+        out[e] = min(world - 1, ((2 * before + n) * world) // (2 * total)) if total > 0 else 0
+        before += n
     return out
+
+
+def owned_edges(edges, rank, world, n_pts, fixed=None):
+    """Edges processed by `rank` (frame.cpp:93: a fixed frame computes no correspondences)."""
+    return [e for e, o in enumerate(edge_owners(edges, n_pts, world, fixed)) if o == rank]
 
 
 def broadcast_unique_id(make_id, rank, device=None):

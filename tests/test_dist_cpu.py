@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from mv_lm_icp_b200 import synth
-from mv_lm_icp_b200.dist import broadcast_unique_id, frame_owner, gather_blocks_by_allreduce, owned_edges
+from mv_lm_icp_b200.dist import broadcast_unique_id, edge_owners, gather_blocks_by_allreduce, owned_edges
 
 
 def _free_port():
@@ -21,7 +21,7 @@ def _worker(rank, world, port, out_dir):
     M = 7
     edges = synth.ring_edges(M, 2)
     fixed = [1] + [0] * (M - 1)
-    mine = owned_edges(edges, rank, world, M, fixed)
+    mine = owned_edges(edges, rank, world, [1000] * M, fixed)
     uid = broadcast_unique_id(lambda: bytes(range(128)), rank)
     assert uid == bytes(range(128))
     rng = np.random.default_rng(1234)                      # same stream on every rank = the "true" per-edge blocks
@@ -43,12 +43,26 @@ def test_two_rank_sharding(tmp_path):
     a, b = (set(np.load(tmp_path / f"owned_{r}.npy").tolist()) for r in range(2))
     assert not (a & b)
     assert a | b == {e for e, (s, d) in enumerate(edges) if s != 0}
-    assert all(frame_owner(edges[e][0], 2, M) == 0 for e in a) and all(frame_owner(edges[e][0], 2, M) == 1 for e in b)
+    assert abs(len(a) - len(b)) <= 1 and max(a) < min(b)             # contiguous runs, balanced
 
 
-def test_owner_is_a_balanced_block_distribution():
+def test_edge_owners_balance_queries():
+    rng = np.random.default_rng(5)
     for M, G in [(20, 1), (20, 2), (20, 4), (20, 8), (40, 4), (64, 8), (5, 8)]:
-        own = [frame_owner(f, G, M) for f in range(M)]
-        assert own == sorted(own) and max(own) <= G - 1
-        counts = np.bincount(own, minlength=G)
-        assert counts.max() - counts[counts > 0].min() <= 1 or M < G
+        edges = synth.ring_edges(M, 2)
+        fixed = [1] + [0] * (M - 1)
+        for n_pts in ([200000] * M, rng.integers(1000, 300000, M).tolist()):
+            own = edge_owners(edges, n_pts, G, fixed)
+            act = [o for o in own if o >= 0]
+            assert all(own[e] == -1 for e, (s, d) in enumerate(edges) if s == 0)
+            assert act == sorted(act) and 0 <= min(act) and max(act) <= G - 1          # contiguous runs in graph order
+            load = np.zeros(G)
+            for e, o in enumerate(own):
+                if o >= 0:
+                    load[o] += n_pts[edges[e][0]]
+            ideal = load.sum() / G
+            assert load.max() <= ideal + max(n_pts)                                    # within one edge of the ideal cut
+    # 20 equal frames over 8 ranks: 38 active edges -> 4 or 5 each (frame-wise sharding would give 6 against 4)
+    own = edge_owners(synth.ring_edges(20, 2), [200000] * 20, 8, [1] + [0] * 19)
+    counts = np.bincount([o for o in own if o >= 0], minlength=8)
+    assert counts.min() >= 4 and counts.max() <= 5

@@ -1,5 +1,6 @@
-"""Sharded path on real GPUs (skipped unless >= 2 devices): frames split over 2 ranks, NCCL all-reduce of the per-edge
-blocks; poses must be BIT-IDENTICAL to the single-GPU run and match the oracle."""
+"""Sharded path on real GPUs (skipped unless >= 2 devices): edges split over 2 ranks (balanced by query count), per-edge pair
+matrices exchanged through peer memory or ncclAllReduce; poses must be BIT-IDENTICAL to the single-GPU run (DESIGN.md
+section 5), and the engine's ownership must be the rule mv_lm_icp_b200/dist.py states."""
 import os
 import socket
 
@@ -35,6 +36,15 @@ def _run(rank, world, port, out_dir, flags):
     for _ in range(3):
         s = eng.icp_round(0.05, mv.PARAM_SE3, mv.COST_P2PLANE, True)
         out.append((eng.get_poses(), s["num_iterations"]))
+    # ownership: get_nn succeeds exactly on the edges dist.edge_owners gives this rank
+    from mv_lm_icp_b200.dist import edge_owners
+    own = edge_owners(edges, [len(p) for p in sc["pts"]], world, [1] + [0] * 5)
+    for e in range(len(edges)):
+        try:
+            eng.get_nn(e); mine = True
+        except RuntimeError:
+            mine = False
+        assert mine == (own[e] == rank), (e, rank, own[e])
     np.save(os.path.join(out_dir, f"poses_{rank}.npy"), np.stack([o[0] for o in out]))
     np.save(os.path.join(out_dir, f"iters_{rank}.npy"), np.array([o[1] for o in out]))
     eng.close()
