@@ -72,6 +72,30 @@ def test_pipeline_round_matches_oracle(oracle):
     eng.close()
 
 
+@pytest.mark.parametrize("n_views", [29, 40])
+def test_many_views_factor_in_global_memory(oracle, n_views):
+    """The reference's default is --limit=40 frames (main_multiview.cpp:34): 6 x 39 = 234 unknowns, whose Cholesky factor no
+    longer fits the 227 KB of shared memory (n <= 166), so lm_step_kernel keeps it in global memory; 29 views = 168 is the
+    first size on that path.  Same parity bar as the small cases, two consecutive rounds."""
+    sc = scene(n_views, 1500, 41)
+    edges = synth.ring_edges(n_views, 2)
+    eng = Engine(); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges)
+    poses = sc["poses_init"].copy()
+    for rnd in range(2):
+        eng.set_poses(poses)
+        s = eng.icp_round(0.05, PARAM_SE3, COST_P2PLANE, True)
+        P = eng.get_poses()
+        ref = oracle_correspond(oracle, sc["pts"], poses, edges)
+        corr = [((r["first"], r["second"]) if r else (np.zeros(0, np.int32), np.zeros(0, np.int32))) for r in ref]
+        w = [np.float32(r["weight"]) if r else np.float32(0) for r in ref]
+        Pref, sref, _ = oracle.optimize(sc["pts"], sc["nor"], poses, edges, corr, w, param=PARAM_SE3, cost=COST_P2PLANE,
+                                        robust=True, threads=8)
+        assert s["num_iterations"] == sref["num_iterations"] and s["termination"] == sref["termination"]
+        assert pose_rel_err(P, Pref) <= TIGHT_TOL
+        poses = Pref
+    eng.close()
+
+
 def test_converges_to_ground_truth():
     """Synthetic exactly-rigid data: 20 rounds bring every pose back to GT (the reference's visual check, README.md:156-188),
     up to the few-mm bias that matching non-overlapping regions with a 5 cm cutoff leaves (the CPU oracle ends at the same place)."""
