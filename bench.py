@@ -122,6 +122,21 @@ def hbm_peak():
 # ======================================================================================================
 # CPU arm: the reference path on the host cores (nanoflann verbatim from oracle/_ref when built, oracle LM port)
 # ======================================================================================================
+def host_threads():
+    """OpenMP threads for the CPU arm: one per PHYSICAL core (hyper-thread siblings slow the static-schedule loops down:
+    measured 27 s vs 4 s per LM round at 128 vs 64 threads on a 64-core box)."""
+    from oracle import oracle as O
+    n = O.max_threads()
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys) if n > 0 else phys
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_rounds(sc, views_sub, n_rounds, cfg, threads):
     """Runs n_rounds outer ICP rounds on the sub-problem made of the first `views_sub` views (ring edges among them),
     with every host thread.  Returns per-round seconds [(corr_s, lm_s)], number of edges, and which NN code ran."""
@@ -154,7 +169,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     sc = load_scene(args.config, cfg["views"], cfg["points"])
     E_full = len([e for e in __import__("mv_lm_icp_b200").synth.ring_edges(cfg["views"], 2) if e[0] != 0])
     views_sub = 3   # frames 0,1,2 -> edges (1,0),(1,2),(2,1)
@@ -330,7 +345,7 @@ def run_ours(args, cfg):
                "time_share": share}
         if world == 1 and not args.no_cpu:
             from oracle import oracle as O
-            th = O.max_threads()
+            th = host_threads()
             tms, E_sub, kind = cpu_rounds(sc, 3, 2, cfg, th)
             E_full = len([e for e in edges if e[0] != 0])
             per_round = float(np.mean([a + b for a, b, _ in tms])) * E_full / E_sub
@@ -338,6 +353,11 @@ def run_ours(args, cfg):
                                    "sample": f"2 rounds of the 3-view sub-problem ({E_sub} of {E_full} edges x {N} queries), extrapolated by edge count; "
                                              f"NN = {'reference nanoflann (oracle/_ref)' if kind == 'ref' else 'oracle KD port'}, LM = oracle port "
                                              f"(Ceres not installable), {th} threads"}
+            # the reference itself is single-threaded: the faithful figure, on one edge, beside the all-core one
+            t1, E1, _ = cpu_rounds(sc, 2, 1, cfg, 1)
+            per_round1 = float(np.mean([a + b for a, b, _ in t1])) * E_full / E1
+            out["cpu_baseline"]["single_thread"] = {"value": 1.0 / per_round1, "unit": "iter/s", "cores": 1,
+                                                    "sample": f"round 0 of the 2-view sub-problem ({E1} of {E_full} edges x {N} queries), extrapolated by edge count"}
         print(json.dumps(out), flush=True)
     eng.close()
     if world > 1:

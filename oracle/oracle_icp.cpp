@@ -286,7 +286,8 @@ struct MvProblem {
     std::vector<double> P((size_t)M * GG * 6);
     if (H) for (int f = 0; f < M; ++f) frame_local_jac(&p[(size_t)f * GG], &P[(size_t)f * GG * 6]);
     int nth = std::max(1, threads);
-    std::vector<double> costs(nth, 0.0);
+    constexpr int CPAD = 16;   // one cache line (and its neighbour) per thread: the accumulators are written every iteration
+    std::vector<double> costs((size_t)nth * CPAD, 0.0);
     std::vector<std::vector<double>> Hs, gs;
     if (H) { Hs.assign(nth, std::vector<double>((size_t)n * n, 0.0)); gs.assign(nth, std::vector<double>(n, 0.0)); }
     for (int e = 0; e < E; ++e) {
@@ -332,12 +333,12 @@ struct MvProblem {
           double sq = 0; for (int q = 0; q < nr; ++q) sq += r[q] * r[q];
           if (robust) {
             double rho[3]; soft_l1(a, sq, rho);
-            costs[tid] += 0.5 * rho[0];
+            costs[(size_t)tid * CPAD] += 0.5 * rho[0];
             if (H) {   // Corrector with rho'' <= 0: scale residuals and Jacobian by sqrt(rho') [ext-knowledge corrector.cc]
               const double sr = std::sqrt(rho[1]);
               for (int q = 0; q < nr; ++q) { r[q] *= sr; for (int l = 0; l < 12; ++l) J[q][l] *= sr; }
             }
-          } else costs[tid] += 0.5 * sq;
+          } else costs[(size_t)tid * CPAD] += 0.5 * sq;
           if (H) {
             double* Ht = Hs[tid].data(); double* gt = gs[tid].data();
             for (int q = 0; q < nr; ++q) {
@@ -357,7 +358,7 @@ struct MvProblem {
         }
       }
     }
-    double cst = 0; for (int t = 0; t < nth; ++t) cst += costs[t];
+    double cst = 0; for (int t = 0; t < nth; ++t) cst += costs[(size_t)t * CPAD];
     *cost_out = cst;
     if (H) {
       std::fill(H, H + (size_t)n * n, 0.0); std::fill(g, g + n, 0.0);
