@@ -83,7 +83,7 @@ struct mvicp_ctx {
   std::vector<EdgeDev> h_edges;
   std::vector<int32_t> edge_owner;   // rank that processes edge e (-1: src frame fixed, nobody)
   DevBuf d_edges, d_xf, d_corr, d_d2, d_count, d_sel, d_hist, d_weight, d_median, d_selcand, d_selcand_n;
-  DevBuf d_knn_tiles, d_eval_tiles, d_edge_tile_begin, d_partial, d_blocks;
+  DevBuf d_knn_tiles, d_eval_tiles, d_edge_tile_begin, d_partial;
   int n_knn_tiles = 0, n_eval_tiles = 0, eval_tile_len = EVAL_TILE;
   int64_t total_slots = 0;
   bool have_corr = false;      // corr[] holds a previous round (usable as seeds)
@@ -207,7 +207,7 @@ void mvicp_destroy(mvicp_ctx* c) {
   for (void* p : c->frame_allocs) cudaFree(p);
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
                     &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
-                    &c->d_blocks, &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
+                    &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
                     &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen};
@@ -368,7 +368,6 @@ static int rebuild_work(mvicp_ctx* c) {
   RET(c->d_eval_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, et.size())));
   RET(c->d_edge_tile_begin.reserve(sizeof(int32_t) * (E + 1)));
   RET(c->d_partial.reserve(sizeof(double) * NBLK * std::max<size_t>(1, et.size())));
-  RET(c->d_blocks.reserve(sizeof(double) * NBLK * E));
   CU(cudaMemcpy(c->d_edges.p, c->h_edges.data(), sizeof(EdgeDev) * E, cudaMemcpyHostToDevice));
   if (!kt.empty()) CU(cudaMemcpy(c->d_knn_tiles.p, kt.data(), sizeof(Tile) * kt.size(), cudaMemcpyHostToDevice));
   if (!et.empty()) CU(cudaMemcpy(c->d_eval_tiles.p, et.data(), sizeof(Tile) * et.size(), cudaMemcpyHostToDevice));
