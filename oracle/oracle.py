@@ -242,6 +242,18 @@ def pairwise(src, dst, nor=None, param=PARAM_SE3, cost=COST_P2P, se3_autodiff=Fa
     return out.reshape(4, 4).T.copy(), summ.asdict()
 
 
+def closed_form(src, dst, nor=None):
+    """Restated ICP_Closedform::pointToPoint (nor is None) / pointToPlane (icp-closedform.cpp:9-54): 4x4 src -> dst."""
+    src = _f64(src).reshape(-1, 3); dst = _f64(dst).reshape(-1, 3)
+    out = np.zeros(16)
+    if nor is None:
+        lib().orc_closed_p2p(_p(src), _p(dst), C.c_int64(len(src)), _p(out))
+    else:
+        nr = _f64(nor).reshape(-1, 3)
+        lib().orc_closed_p2plane(_p(src), _p(dst), _p(nr), C.c_int64(len(src)), _p(out))
+    return out.reshape(4, 4).T.copy()
+
+
 def default_options():
     o = LmOptions()
     lib().orc_default_lm_options(C.byref(o))

@@ -638,6 +638,66 @@ int orc_pairwise(const double* src, const double* dst, const double* nor, int64_
   return rc;
 }
 
+// ---- closed-form pairwise solvers (src/internal/icp-closedform.cpp:9-54) -------
+// pointToPoint (:9-26): centroids, K = sum (q - qbar)(p - pbar)^T, R = U V^T from the SVD of K, and -- as the reference does
+// it -- `R.col(2) *= -1` when det R < 0 (the third column of R, not of U); t = qbar - R pbar.
+// U V^T is the orthogonal polar factor of K, unique for non-singular K whatever the SVD's sign/order conventions are
+// [ext-knowledge Eigen JacobiSVD], computed here as K V diag(1/sigma) V^T with V, sigma^2 from the symmetric
+// eigen-decomposition of K^T K.
+void orc_closed_p2p(const double* src, const double* dst, int64_t n, double* pose16_out) {
+  double pb[3] = {0, 0, 0}, qb[3] = {0, 0, 0};
+  for (int64_t i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) { pb[a] += src[3 * i + a]; qb[a] += dst[3 * i + a]; }
+  for (int a = 0; a < 3; ++a) { pb[a] /= (double)n; qb[a] /= (double)n; }
+  double K[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int64_t i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) K[a][b] += (dst[3 * i + a] - qb[a]) * (src[3 * i + b] - pb[b]);
+  double S[3][3], w[3], V[3][3];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { S[a][b] = 0; for (int c = 0; c < 3; ++c) S[a][b] += K[c][a] * K[c][b]; }
+  eig3(S, w, V);
+  double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < 3; ++j) {
+    const double sg = std::sqrt(std::max(w[j], 0.0));
+    double u[3]; for (int a = 0; a < 3; ++a) { u[a] = 0; for (int c = 0; c < 3; ++c) u[a] += K[a][c] * V[c][j]; u[a] /= sg; }   // column j of U
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[a][b] += u[a] * V[b][j];
+  }
+  const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                     R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+  if (det < 0) for (int a = 0; a < 3; ++a) R[a][2] *= -1;      // icp-closedform.cpp:20-22
+  for (int i = 0; i < 16; ++i) pose16_out[i] = 0; pose16_out[15] = 1;
+  for (int a = 0; a < 3; ++a) {
+    for (int b = 0; b < 3; ++b) pose16_out[4 * b + a] = R[a][b];
+    pose16_out[12 + a] = qb[a] - (R[a][0] * pb[0] + R[a][1] * pb[1] + R[a][2] * pb[2]);
+  }
+}
+
+// pointToPlane (:30-54): linearised rotation, 6x6 normal equations C x = d with x = (alpha, beta, gamma, t),
+// rows [p x n ; n], d = -sum [p x n ; n] ((p - q).n), solved by LDL^T; R = Rx(alpha) Ry(beta) Rz(gamma), t = x[3..5].
+void orc_closed_p2plane(const double* src, const double* dst, const double* nor, int64_t n, double* pose16_out) {
+  double Cm[6][6] = {{0}}, d[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t i = 0; i < n; ++i) {
+    const double* p = src + 3 * i; const double* q = dst + 3 * i; const double* nn = nor + 3 * i;
+    const double a[6] = {p[1] * nn[2] - p[2] * nn[1], p[2] * nn[0] - p[0] * nn[2], p[0] * nn[1] - p[1] * nn[0], nn[0], nn[1], nn[2]};
+    const double sum = (p[0] - q[0]) * nn[0] + (p[1] - q[1]) * nn[1] + (p[2] - q[2]) * nn[2];
+    for (int r = 0; r < 6; ++r) { for (int c = 0; c < 6; ++c) Cm[r][c] += a[r] * a[c]; d[r] -= a[r] * sum; }
+  }
+  // LDL^T without pivoting (C is symmetric positive definite for a non-degenerate surface)
+  double L[6][6] = {{0}}, D[6];
+  for (int j = 0; j < 6; ++j) {
+    double dj = Cm[j][j]; for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k] * D[k];
+    D[j] = dj; L[j][j] = 1;
+    for (int i = j + 1; i < 6; ++i) { double v = Cm[i][j]; for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k]; L[i][j] = v / dj; }
+  }
+  double y[6], x[6];
+  for (int i = 0; i < 6; ++i) { y[i] = d[i]; for (int k = 0; k < i; ++k) y[i] -= L[i][k] * y[k]; }
+  for (int i = 5; i >= 0; --i) { x[i] = y[i] / D[i]; for (int k = i + 1; k < 6; ++k) x[i] -= L[k][i] * x[k]; }
+  const double ca = std::cos(x[0]), sa = std::sin(x[0]), cb = std::cos(x[1]), sb = std::sin(x[1]), cg = std::cos(x[2]), sg = std::sin(x[2]);
+  const double R[3][3] = {{cb * cg, -cb * sg, sb},
+                          {sa * sb * cg + ca * sg, -sa * sb * sg + ca * cg, -sa * cb},
+                          {-ca * sb * cg + sa * sg, ca * sb * sg + sa * cg, ca * cb}};
+  for (int i = 0; i < 16; ++i) pose16_out[i] = 0; pose16_out[15] = 1;
+  for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) pose16_out[4 * b + a] = R[a][b]; pose16_out[12 + a] = x[3 + a]; }
+}
+
 // ---- small math exports for known-answer tests ---------------------------------------------------
 void orc_se3_exp(const double* tangent6, double* out7) { se3_exp(tangent6, out7); }
 void orc_se3_mul(const double* a7, const double* b7, double* out7) { se3_mul(a7, b7, out7); }
