@@ -86,6 +86,9 @@ def test_pairwise_driver_cli(tmp_path):
     r = subprocess.run([BIN_PAIR, f"--cloud={tmp_path}/c.xyz"], capture_output=True, text=True)
     assert r.returncode in (0, 2)                            # 2 = no CUDA device here
     assert len(r.stdout.splitlines()) >= 10                  # the first ten points are echoed (main_pairwise.cpp:36-39)
+    # the closed-form comparison row runs on the host (apps/closed_form.hpp): exact for known correspondences
+    m = re.search(r"closed form\s+diff_tra:([0-9.e+-]+)\t diff_rot_degrees:([0-9.e+-]+)", r.stdout)
+    assert m and float(m.group(1)) < 1e-12 and float(m.group(2)) < 1e-5
 
 
 @pytest.mark.gpu
@@ -106,4 +109,6 @@ def test_pairwise_driver_recovers_known_transform(tmp_path, p2plane):
         assert np.linalg.norm(E[:3, 3] - P[:3, 3]) < 1e-8, (k, E, P)
         assert np.degrees(np.arccos(np.clip((np.trace(E[:3, :3].T @ P[:3, :3]) - 1) / 2, -1, 1))) < 1e-5
     m = re.findall(r"diff_tra:([0-9.e+-]+)\t diff_rot_degrees:([0-9.e+-]+)", r.stdout)
-    assert len(m) == 3 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m)
+    assert len(m) == 4 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m[1:])   # m[0] = closed form (linearised for p2plane)
+    if not p2plane:
+        assert float(m[0][0]) < 1e-12
