@@ -7,6 +7,10 @@ bunny_pair.npz   config 1 of BASELINE.json: the reference's own sample scans sam
                  /root/reference/include/nanoflann.hpp) for edge 1 -> 0 under those poses, i.e. the pinned answer of
                  Frame::computeClosestPointsToNeighbours' inner loop (frame.cpp:129-138);
                  + first/second/dist/weight of frame.cpp:140-176 from those.
+dino_pair.npz    the reference's second sample set, samples/dinosaur/cloud_{1,2}.xyz with pose_{1,2}.txt: millimetre units
+                 (|coordinates| up to 686, NN distances of tens of mm), 5-digit pose matrices (not exactly orthonormal):
+                 edge 2 -> 1, reference nanoflann answer + frame.cpp:140-176 at cutoff 25 (the default 0.05 m is meaningless
+                 in mm); pins the fp32 screening bound at a different coordinate magnitude.
 lm_golden.npz    oracle LM outputs (final poses, iteration trace) on a small seeded synthetic scene for every
                  parameterisation x cost; pins the oracle against accidental change (NOT against Ceres: unpinned).
 sophus_vectors.npz  the SE3 group elements / tangents of ext/sophus-ceres/test/core/test_se3.cpp:40-82 (values only).
@@ -35,6 +39,18 @@ def bunny_pair():
                         nor1=c[1][:, 3:6], pose0=P[0], pose1=P[1], nn_idx=idx, nn_d2=d2, first=first, second=second,
                         dist=dist, weight=w, median=med)
     print("bunny_pair:", c[0].shape, c[1].shape, "inliers", len(first), "weight", w)
+
+
+def dino_pair():
+    D = "/root/reference/samples/dinosaur"
+    c = [np.loadtxt(f"{D}/cloud_{i}.xyz") for i in (1, 2)]
+    P = [np.loadtxt(f"{D}/pose_{i}.txt") for i in (1, 2)]
+    ref = O.KdIndex(c[0][:, :3], "ref")
+    idx, d2 = ref.closest_points(c[1][:, :3], P[1], P[0])
+    first, second, dist, w, med = O.filter_edge(idx, d2, np.float32(25.0))
+    np.savez_compressed(os.path.join(OUT, "dino_pair.npz"), pts0=c[0][:, :3], nor0=c[0][:, 3:6], pts1=c[1][:, :3], nor1=c[1][:, 3:6],
+                        pose0=P[0], pose1=P[1], nn_idx=idx, nn_d2=d2, first=first, second=second, dist=dist, weight=w, median=med)
+    print("dino_pair:", c[0].shape, c[1].shape, "inliers", len(first), "weight", w)
 
 
 def lm_golden():
@@ -74,4 +90,4 @@ def sophus_vectors():
 
 
 if __name__ == "__main__":
-    bunny_pair(); lm_golden(); sophus_vectors()
+    bunny_pair(); dino_pair(); lm_golden(); sophus_vectors()

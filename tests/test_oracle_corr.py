@@ -49,6 +49,21 @@ def test_golden_bunny_pair(oracle, golden_dir):
         assert np.array_equal(ri, g["nn_idx"]) and np.array_equal(rd, g["nn_d2"])
 
 
+def test_golden_dinosaur_pair(oracle, golden_dir):
+    """The reference's second sample set (millimetre units, |x| up to 686, NN distances of tens of mm, 5-digit pose
+    matrices): golden = reference nanoflann, cutoff 25 (tests/golden/make_golden.py:dino_pair)."""
+    g = np.load(f"{golden_dir}/dino_pair.npz")
+    idx, d2 = oracle.KdIndex(g["pts0"], "kd").closest_points(g["pts1"], g["pose1"], g["pose0"], threads=4)
+    assert np.array_equal(d2.view(np.uint64), g["nn_d2"].view(np.uint64))
+    assert np.array_equal(idx, g["nn_idx"])
+    f, s, dist, w, med = oracle.filter_edge(idx, d2, np.float32(25.0))
+    assert np.array_equal(f, g["first"]) and np.array_equal(s, g["second"]) and np.array_equal(dist, g["dist"])
+    assert np.float32(w) == g["weight"] and med == g["median"] and 0 < len(f) < len(idx)
+    if oracle.ref_lib() is not None:
+        ri, rd = oracle.KdIndex(g["pts0"], "ref").closest_points(g["pts1"], g["pose1"], g["pose0"])
+        assert np.array_equal(ri, g["nn_idx"]) and np.array_equal(rd, g["nn_d2"])
+
+
 def test_filter_semantics(oracle):
     d2 = np.array([1e-6, 4e-6, 0.0025000001, 9e-6, 0.0024, 1.0])     # sqrt: .001 .002 >.05 .003 .049 1
     idx = np.arange(6, dtype=np.int32)[::-1].copy()

@@ -1,13 +1,58 @@
 // tools/knn_host_check.cpp -- compiles the engine's own csrc/knn.cuh + tree_build.h with g++ (tools/hostshim) and runs the
 // SEARCH TEXT (nn_query_init / nn_search / nn_search_warp with a one-lane warp) on the host against a brute force in the
-// reference's operation order.  Usage: knn_host_check <n_points> <n_queries> <seed> <mode>   mode 0: fp32-exact coordinates
+// reference's operation order, or (--file <bin>) against a golden answer.  Usage: knn_host_check <n_points> <n_queries> <seed> <mode>   mode 0: fp32-exact coordinates
 // (fp32 storage), 1: arbitrary doubles (fp64 records + rounded fp32 screening copy).  Exit code 0 = all queries exact.
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 #include <vector>
 #include "../mv_lm_icp_b200/csrc/knn.cuh"
 #include "../mv_lm_icp_b200/csrc/tree_build.h"
+
+// frame from explicit points (fp64 records + rounded fp32 screening copy, as mvicp_set_frames stores non-fp32 data)
+struct HostFrame {
+  HostFrameBuild hb; std::vector<float4> sf; std::vector<double4a> sd; FrameDev fd{};
+  HostFrame(const double* pts, int n, bool f32) {
+    build_frame(pts, n, hb);
+    const int64_t npad = ((n + LEAF - 1) / LEAF) * LEAF;
+    sf.resize(npad); sd.resize(npad);
+    for (int64_t i = 0; i < npad; ++i) {
+      const int32_t w = i < n ? hb.order[i] : INT32_MAX; const int64_t j = i < n ? hb.order[i] : 0;
+      float4 r; double4a q;
+      if (i < n) { r.x = (float)pts[3 * j]; r.y = (float)pts[3 * j + 1]; r.z = (float)pts[3 * j + 2]; q.x = pts[3 * j]; q.y = pts[3 * j + 1]; q.z = pts[3 * j + 2]; }
+      else { r.x = r.y = r.z = INFINITY; q.x = q.y = q.z = INFINITY; }
+      std::memcpy(&r.w, &w, 4); const long long wl = w; std::memcpy(&q.w, &wl, 8);
+      sf[i] = r; sd[i] = q;
+    }
+    fd.pts_s = f32 ? (const void*)sf.data() : (const void*)sd.data(); fd.pts_sf = sf.data(); fd.boxes = hb.boxes.data(); fd.faces = hb.faces.data();
+    fd.pos_of = hb.pos_of.data(); fd.n = n; fd.n_leaf_pad = hb.n_leaf_pad; fd.depth = hb.depth; fd.absmax = hb.absmax;
+  }
+};
+
+// file mode: int64 n, int64 nq, pts[3n], queries[3nq] (already in the frame's coordinates), want_idx[nq] (int32), want_d2[nq]:
+// a golden answer (e.g. the reference's nanoflann on a real scan, tests/test_knn_host.py) instead of the local brute force
+static int run_file(const char* path) {
+  FILE* f = std::fopen(path, "rb"); if (!f) { std::printf("cannot open %s\n", path); return 1; }
+  int64_t n = 0, nq = 0; if (std::fread(&n, 8, 1, f) != 1 || std::fread(&nq, 8, 1, f) != 1) return 1;
+  std::vector<double> pts(3 * n), q(3 * nq), wd(nq); std::vector<int32_t> wi(nq);
+  if (std::fread(pts.data(), 8, 3 * n, f) != (size_t)(3 * n) || std::fread(q.data(), 8, 3 * nq, f) != (size_t)(3 * nq) ||
+      std::fread(wi.data(), 4, nq, f) != (size_t)nq || std::fread(wd.data(), 8, nq, f) != (size_t)nq) return 1;
+  std::fclose(f);
+  HostFrame F(pts.data(), (int)n, false);
+  int bad = 0; std::vector<int> prev(nq, -1);
+  for (int pass = 0; pass < 2; ++pass)        // pass 1 is seeded with pass 0's answers, as round r+1 is by round r
+    for (int64_t i = 0; i < nq; ++i)
+      for (int sched = 0; sched < 2; ++sched) {
+        NNQuery s2; nn_query_init(s2, q[3 * i], q[3 * i + 1], q[3 * i + 2], F.fd.absmax);
+        const int start_leaf = pass == 0 ? -1 : F.hb.pos_of[prev[i]] / LEAF;
+        if (sched == 0) nn_search<false, NNQuery>(F.fd, s2, start_leaf); else nn_search_warp<false>(F.fd, s2, start_leaf, true);
+        if (s2.bi != wi[i] || s2.best != wd[i]) { if (++bad < 10) std::printf("MISMATCH q %lld pass %d sched %d: got (%d, %.17g) want (%d, %.17g)\n", (long long)i, pass, sched, s2.bi, s2.best, wi[i], wd[i]); }
+        prev[i] = s2.bi;
+      }
+  std::printf("file %s: n %lld queries %lld: %d mismatches\n", path, (long long)n, (long long)nq, bad);
+  return bad;
+}
 
 template <bool F32> static int run(int n, int nq, unsigned seed) {
   std::mt19937_64 rng(seed);
@@ -63,6 +108,7 @@ template <bool F32> static int run(int n, int nq, unsigned seed) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 2 && std::string(argv[1]) == "--file") return run_file(argv[2]) ? 1 : 0;
   const int n = argc > 1 ? atoi(argv[1]) : 5000, nq = argc > 2 ? atoi(argv[2]) : 2000;
   const unsigned seed = argc > 3 ? (unsigned)atoi(argv[3]) : 1u; const int mode = argc > 4 ? atoi(argv[4]) : 0;
   return (mode == 0 ? run<true>(n, nq, seed) : run<false>(n, nq, seed)) ? 1 : 0;
