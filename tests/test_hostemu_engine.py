@@ -1,0 +1,104 @@
+"""The engine's own sources -- mvicp.cu and every kernel header -- compiled by g++ against the miniature CUDA model in
+tools/hostemu (TEST INFRASTRUCTURE: fibers for CTA threads, host memory for device memory) and driven through the same C ABI
+and the same parity tests as the GPU suite, at small sizes.  This exercises the LOGIC of the whole device path (search,
+median select, residual/Jacobian reduction, LM state machine, general path, normals) on the CPU; the hardware's roundings,
+memory model and the multi-GPU exchange are covered only by `pytest -m gpu`.  The product never loads this library."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools", "hostemu"))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    """Builds libmvicp_hostemu.so and points the ctypes binding at it for the duration of this module."""
+    import build_hostemu
+    from mv_lm_icp_b200 import _lib
+    so = build_hostemu.build()
+    lib = C.CDLL(so); lib.mvicp_last_error.restype = C.c_char_p
+    saved = _lib._lib
+    _lib._lib = lib
+    yield lib
+    _lib._lib = saved
+
+
+def test_exports_every_abi_symbol(emu):
+    from mv_lm_icp_b200 import _lib
+    for name in _lib.EXPORTS:
+        assert hasattr(emu, name), name
+
+
+def test_correspondence_step(emu, oracle, golden_dir):
+    import test_gpu_corr as T
+    T.test_synthetic_bit_exact(oracle, 4, 5000, 21)
+    T.test_seed_and_schedule_do_not_change_results(oracle)
+    T.test_real_bunny_pair_fp64_storage(oracle, golden_dir)
+    T.test_real_dinosaur_pair_mm_units(golden_dir)
+    T.test_edge_cases(oracle)
+    T.test_median_with_masses_of_near_equal_distances(oracle)
+    T.test_closest_point_api(oracle)
+
+
+@pytest.mark.parametrize("param", [0, 1, 2])
+@pytest.mark.parametrize("cost", [0, 1, 2])
+@pytest.mark.parametrize("robust", [False, True])
+def test_lm_step_matches_oracle(emu, oracle, golden_dir, param, cost, robust):
+    import test_gpu_lm as T
+    T.test_optimize_matches_oracle(oracle, golden_dir, param, cost, robust)
+
+
+def test_lm_pipeline_pairwise_and_general_path(emu, oracle, golden_dir):
+    import test_gpu_lm as T
+    T.test_pipeline_round_matches_oracle(oracle)
+    for name, param, cost in (("pointToPoint_CeresAngleAxis", 0, 0), ("pointToPoint_EigenQuaternion", 1, 0), ("pointToPoint_SophusSE3", 2, 0),
+                              ("pointToPlane_CeresAngleAxis", 0, 1), ("pointToPlane_EigenQuaternion", 1, 1), ("pointToPlane_SophusSE3", 2, 1)):
+        T.test_pairwise_known_answer(oracle, golden_dir, name, param, cost)
+    T.test_real_bunny_nonrigid_poses(oracle, golden_dir, 2, 1)      # non-unit quaternions: general frame model
+    T.test_real_bunny_nonrigid_poses(oracle, golden_dir, 1, 0)
+
+
+@pytest.mark.parametrize("n_views", [29, 40])
+def test_lm_many_views_global_factor(emu, oracle, n_views):
+    import test_gpu_lm as T
+    T.test_many_views_factor_in_global_memory(oracle, n_views)
+
+
+def test_normals(emu, oracle, golden_dir):
+    import test_gpu_normals as T
+    T.test_normals_match_oracle_synthetic(oracle)
+    T.test_normals_real_scan_and_lm_uses_them(oracle, golden_dir)
+
+
+def test_headless_driver_on_the_emulated_engine(emu, tmp_path):
+    """apps/multiview_main.cpp linked against the emulated library: the reference's file formats, flags and loop end to end,
+    bit-identical to the Python mirror of the same loop (what tests/test_app_multiview.py checks on the GPU)."""
+    import subprocess
+    import test_app_multiview as A
+    from helpers import scene
+    from mv_lm_icp_b200 import Frame, ICP_Ceres
+    build_dir = os.path.join(ROOT, "tools", "hostemu", "_build")
+    exe = os.path.join(build_dir, "multiview_hostemu")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-o", exe, os.path.join(ROOT, "apps", "multiview_main.cpp"), "-L" + build_dir,
+                    "-lmvicp_hostemu", "-Wl,-rpath," + build_dir], check=True)
+    sc = scene(4, 1500, 17)
+    A._write_scene(str(tmp_path), sc)
+    out = tmp_path / "out"; out.mkdir()
+    r = subprocess.run([exe, f"--dir={tmp_path}", "--step=1", "--knn=2", "--rounds=3", f"--out={out}"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = [np.loadtxt(out / f"pose_out_{i}.txt") for i in range(4)]
+    frames = [Frame(p, n, pose=P) for p, n, P in zip(sc["pts"], sc["nor"], sc["poses_init"])]
+    icp = ICP_Ceres(frames)
+    icp.recomputeNormals(10)
+    frames[0].fixed = True
+    icp.computePoseNeighbours(2)
+    for _ in range(3):
+        icp.computeClosestPoints(0.05)
+        icp.ceresOptimizer_sophusSE3(True, True)
+    for i in range(4):
+        assert np.array_equal(got[i], frames[i].pose), i
+    icp.engine.close()
