@@ -50,6 +50,8 @@ static std::vector<Fiber> fibers; static int cur = -1, n_threads = 0;
 static const std::function<void()>* body = nullptr;
 static std::vector<char> dyn; static long long warp_slot[64][32]; static int vote_slot[64][32];
 static const size_t STACK = 256 * 1024;
+static std::vector<int> perm; static unsigned long long rng_state = 0x9E3779B97F4A7C15ULL;
+static const int order_mode = []() { const char* e = std::getenv("HOSTEMU_ORDER"); return !e ? 0 : (e[0] == 'r' && e[1] == 'e' ? 1 : (e[0] == 'r' ? 2 : 0)); }();
 inline void* dyn_smem() { return dyn.data(); }
 #if defined(__x86_64__)
 inline void to_sched() { hostemu_switch(&fibers[cur].sp, sched_sp); }
@@ -80,7 +82,14 @@ inline void run_block() {
   std::memset(vote_slot, 0, sizeof vote_slot);
   while (true) {
     bool progressed = false, alive = false;
-    for (int t = 0; t < n; ++t) if (fibers[t].state == RUN) { cur = t; set_ids(t); to_fiber(t); progressed = true; }
+    // scheduling order between two barriers: ascending thread index, descending (HOSTEMU_ORDER=reverse) or a fresh
+    // pseudo-random permutation every phase (HOSTEMU_ORDER=random): code that lacks a barrier passes under one order at most
+    for (int i = 0; i < n; ++i) {
+      int t = i;
+      if (order_mode == 1) t = n - 1 - i;
+      else if (order_mode == 2) { if (i == 0) { perm.resize(n); for (int k = 0; k < n; ++k) perm[k] = k; for (int k = n - 1; k > 0; --k) { rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL; std::swap(perm[k], perm[(rng_state >> 33) % (unsigned)(k + 1)]); } } t = perm[i]; }
+      if (fibers[t].state == RUN) { cur = t; set_ids(t); to_fiber(t); progressed = true; }
+    }
     // release barriers whose participants (all threads that have not returned) have all arrived
     bool all_block = true; int n_wait = 0;
     for (int t = 0; t < n; ++t) { if (fibers[t].state == DONE) continue; alive = true; if (fibers[t].state != AT_BLOCK) all_block = false; else ++n_wait; }
