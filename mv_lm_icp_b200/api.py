@@ -17,6 +17,7 @@ TERMINATION = ["FUNCTION_TOLERANCE", "GRADIENT_TOLERANCE", "PARAMETER_TOLERANCE"
 FLAG_NO_SEED = 1
 FLAG_NCCL_ONLY = 2
 FLAG_WARP_SEARCH = 4
+FLAG_GRAPH_WALK = 8
 
 
 def _p(a, t=C.c_double):

@@ -25,6 +25,7 @@
 #include "se3_math.cuh"
 #include "select.cuh"
 #include "types.cuh"
+#include "walk.cuh"
 
 using namespace mv;
 
@@ -75,6 +76,8 @@ struct mvicp_ctx {
   std::vector<int64_t> n_pts;
   std::vector<FrameDev> h_frames;
   std::vector<void*> frame_allocs;
+  DevBuf d_walk;               // WalkDev per frame (MVICP_FLAG_GRAPH_WALK only)
+  bool walk_ready = false;
   DevBuf d_frames, d_poses;
   std::vector<uint8_t> fixed;
   std::vector<double> h_poses;   // mirror of the last set/get (pose graph construction is host side)
@@ -210,7 +213,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_walk};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -293,6 +296,32 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
   CU(cudaMemcpy(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * M, cudaMemcpyHostToDevice));
   c->fixed.assign(M, 0); c->fixed[0] = 1;
   c->E = 0; c->h_edges.clear(); c->have_corr = false;
+  c->walk_ready = false;
+  if (c->flags & MVICP_FLAG_GRAPH_WALK) {   // experimental: neighbour lists + certificate radii of every cloud (walk.cuh)
+    std::vector<WalkDev> hw(M);
+    for (int f = 0; f < M; ++f) {
+      const int n = (int)n_pts[f], k = WALK_K + 2;
+      double* d_nor = nullptr; int32_t *d_nn = nullptr, *d_nbr = nullptr; double* d_r2 = nullptr;
+      CU(cudaMalloc(&d_nor, sizeof(double) * 3 * (size_t)n)); CU(cudaMalloc(&d_nn, sizeof(int32_t) * (size_t)k * n));
+      CU(cudaMalloc(&d_nbr, sizeof(int32_t) * (size_t)WALK_K * n)); c->frame_allocs.push_back(d_nbr);
+      CU(cudaMalloc(&d_r2, sizeof(double) * (size_t)n)); c->frame_allocs.push_back(d_r2);
+      if (f32) {
+        normals_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, k, d_nor, d_nn);
+        walk_build_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, d_nn, d_nbr, d_r2);
+      } else {
+        normals_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, k, d_nor, d_nn);
+        walk_build_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, d_nn, d_nbr, d_r2);
+      }
+      c->stats.kernel_launches += 2;
+      CU(cudaStreamSynchronize(c->stream));
+      cudaFree(d_nor); cudaFree(d_nn);
+      hw[f] = WalkDev{d_nbr, d_r2};
+    }
+    RET(c->d_walk.reserve(sizeof(WalkDev) * M));
+    CU(cudaMemcpy(c->d_walk.p, hw.data(), sizeof(WalkDev) * M, cudaMemcpyHostToDevice));
+    CU(cudaGetLastError());
+    c->walk_ready = true;
+  }
   return MVICP_OK;
 }
 
@@ -427,10 +456,16 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
   if (c->n_knn_tiles) {
-    auto kern = (c->flags & MVICP_FLAG_WARP_SEARCH) ? knn_kernel<F32, true> : knn_kernel<F32, false>;
-    kern<<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
-        c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
-        c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh);
+    if (seed && c->walk_ready) {   // experimental: neighbour-graph walk with certificate, tree search as fallback (walk.cuh)
+      knn_walk_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
+          c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
+          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, c->d_walk.as<WalkDev>());
+    } else {
+      auto kern = (c->flags & MVICP_FLAG_WARP_SEARCH) ? knn_kernel<F32, true> : knn_kernel<F32, false>;
+      kern<<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
+          c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
+          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh);
+    }
   }
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);

@@ -50,7 +50,7 @@ def test_exports_every_abi_symbol(emu):
 def test_correspondence_step(emu, oracle, golden_dir):
     import test_gpu_corr as T
     T.test_synthetic_bit_exact(oracle, 4, 5000, 21)
-    T.test_seed_and_schedule_do_not_change_results(oracle)
+    T.test_seed_and_schedule_do_not_change_results(oracle, extra_flags=(T.FLAG_GRAPH_WALK, T.FLAG_GRAPH_WALK | T.FLAG_WARP_SEARCH))
     T.test_real_bunny_pair_fp64_storage(oracle, golden_dir)
     T.test_real_dinosaur_pair_mm_units(golden_dir)
     T.test_edge_cases(oracle)
@@ -125,3 +125,55 @@ def test_headless_driver_on_the_emulated_engine(emu, tmp_path):
     for i in range(4):
         assert np.array_equal(got[i], frames[i].pose), i
     icp.engine.close()
+
+
+def test_graph_walk_is_bit_identical(emu, oracle, golden_dir):
+    """MVICP_FLAG_GRAPH_WALK (csrc/walk.cuh, experimental): seeded rounds answer most queries by a certified walk on the dst
+    cloud's neighbour graph.  Same matches, same distances, same poses as the default search -- over ICP rounds that go
+    from far (certificates fail, tree fallback) to converged (certificates hold), on fp32 and fp64 storage, with exact
+    duplicates and with clouds too small to have neighbour lists."""
+    from helpers import scene
+    from mv_lm_icp_b200 import Engine, synth
+    from mv_lm_icp_b200.api import FLAG_GRAPH_WALK
+    sc = scene(4, 3001, 27)
+    edges = synth.ring_edges(4, 2)
+    runs = []
+    for flags in (0, FLAG_GRAPH_WALK):
+        eng = Engine(flags=flags); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
+        out = []
+        for rnd in range(6 if emu.order == "ascending" else 3):
+            s = eng.icp_round(0.05, 2, 1, True)
+            out.append((eng.get_poses(), s["num_iterations"], [eng.get_nn(e) for e in range(len(edges)) if edges[e][0] != 0]))
+        runs.append(out); eng.close()
+    for (P0, it0, nn0), (P1, it1, nn1) in zip(*runs):
+        assert it0 == it1 and np.array_equal(P0.view(np.uint64), P1.view(np.uint64))
+        for (i0, d0), (i1, d1) in zip(nn0, nn1):
+            assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
+    # fp64 storage, non-rigid poses, real scan (quantised coordinates): three slightly different poses, seeded
+    g = np.load(f"{golden_dir}/bunny_pair.npz")
+    res = []
+    for flags in (0, FLAG_GRAPH_WALK):
+        eng = Engine(flags=flags); eng.set_frames([g["pts0"], g["pts1"]], [g["nor0"], g["nor1"]]); eng.set_graph([(1, 0)])
+        out = []
+        for k in range(3):
+            P1 = g["pose1"].copy(); P1[:3, 3] += 2e-4 * k
+            eng.set_poses([g["pose0"], P1]); eng.correspond(0.05); out.append(eng.get_nn(0))
+        res.append(out); eng.close()
+    assert np.array_equal(res[0][0][0], g["nn_idx"])
+    for (i0, d0), (i1, d1) in zip(*res):
+        assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
+    # exact duplicates (distance ties -> lowest index) and clouds with fewer than ten points (no certificate possible)
+    rng = np.random.default_rng(2)
+    a = (rng.normal(size=(400, 3)) * 0.01).astype(np.float32).astype(np.float64); a[100:140] = a[0:40]
+    b = a[::3] + np.float32(1e-4); tiny = a[:7].copy()
+    res = []
+    for flags in (0, FLAG_GRAPH_WALK):
+        eng = Engine(flags=flags); eng.set_frames([a, b.astype(np.float32).astype(np.float64), tiny], None); eng.set_graph([(1, 0), (1, 2), (2, 0)])
+        eng.set_poses([np.eye(4)] * 3, [1, 0, 0])
+        out = []
+        for k in range(3):
+            eng.correspond(0.05); out.append([eng.get_nn(e) for e in range(3)])
+        res.append(out); eng.close()
+    for r0, r1 in zip(*res):
+        for (i0, d0), (i1, d1) in zip(r0, r1):
+            assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
