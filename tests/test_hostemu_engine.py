@@ -125,6 +125,17 @@ def test_headless_driver_on_the_emulated_engine(emu, tmp_path):
     for i in range(4):
         assert np.array_equal(got[i], frames[i].pose), i
     icp.engine.close()
+    # apps/pairwise_main.cpp: the known-answer benchmark, all three solvers + the closed-form row
+    import re
+    exe2 = os.path.join(build_dir, "pairwise_hostemu")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-o", exe2, os.path.join(ROOT, "apps", "pairwise_main.cpp"), "-L" + build_dir,
+                    "-lmvicp_hostemu", "-Wl,-rpath," + build_dir], check=True)
+    A._write_cloud(tmp_path / "c.xyz", sc["pts"][0], sc["nor"][0])
+    for extra in ([], ["--pointToPlane"]):
+        r = subprocess.run([exe2, f"--cloud={tmp_path}/c.xyz"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        m = re.findall(r"diff_tra:([0-9.e+-]+)\t diff_rot_degrees:([0-9.e+-]+)", r.stdout)
+        assert len(m) == 4 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m[1:])
 
 
 def test_graph_walk_is_bit_identical(emu, oracle, golden_dir):
