@@ -455,11 +455,14 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
+  bool hist0_done = false;   // the walk kernel delivers the select's first histogram itself
   if (c->n_knn_tiles) {
     if (seed && c->walk_ready) {   // experimental: neighbour-graph walk with certificate, tree search as fallback (walk.cuh)
       knn_walk_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
           c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
-          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, c->d_walk.as<WalkDev>());
+          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, c->d_walk.as<WalkDev>(),
+          c->d_hist.as<unsigned int>());
+      hist0_done = true;
     } else {
       auto kern = (c->flags & MVICP_FLAG_WARP_SEARCH) ? knn_kernel<F32, true> : knn_kernel<F32, false>;
       kern<<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
@@ -474,14 +477,15 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   c->stats.kernel_launches += 1;
   const int shifts[2] = {53, 42};
   for (int p = 0; p < 2; ++p) {
-    if (c->n_eval_tiles)
+    const bool have = p == 0 && hist0_done;
+    if (c->n_eval_tiles && !have)
       select_hist_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(
           c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len, c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
           c->d_sel.as<SelState>(), shifts[p], 11, c->d_hist.as<unsigned int>());
     select_pick_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_hist.as<unsigned int>(), shifts[p], p == 0, 0,
                                                          c->d_weight.as<float>(), c->d_median.as<double>(),
                                                          c->d_count.as<unsigned long long>());
-    c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
+    c->stats.kernel_launches += 1 + ((c->n_eval_tiles && !have) ? 1 : 0);
   }
   if (c->n_eval_tiles)
     select_collect_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(

@@ -10,10 +10,12 @@
 //           arg-min under the engine's order (fp64 distance in the reference's operation order, then lowest index).
 // With converged poses the certificate holds for ~93 % of the queries of the Bunny workload after 0-1 moves
 // (tools/walk_rate.py); the others -- far matches, open boundaries, exhausted moves -- are compacted within the CTA and run
-// the tree search, densely packed into its first warps, starting at the leaf where the walk stopped.
+// the tree search, densely packed into its first warps, starting at the leaf where the walk stopped.  The kernel also produces
+// the first histogram of the median select (bits 63:53 of the inlier distances), which saves that pass over the results.
 #pragma once
 #include "knn.cuh"
 #include "normals.cuh"
+#include "select.cuh"
 
 namespace mv {
 
@@ -49,12 +51,15 @@ template <bool F32>
 __global__ void __launch_bounds__(KNN_TILE)
 knn_walk_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
                 const Tile* __restrict__ tiles, int32_t* __restrict__ corr, double* __restrict__ d2out,
-                const int32_t* __restrict__ seed, double thresh, const WalkDev* __restrict__ walk) {
+                const int32_t* __restrict__ seed, double thresh, const WalkDev* __restrict__ walk,
+                unsigned int* __restrict__ hist /* [E][SEL_BINS]: first pass of the median select, fused (select.cuh) */) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ EdgeXf sx;
   __shared__ int s_fail[KNN_TILE], s_start[KNN_TILE];
   __shared__ int s_nfail;
+  __shared__ unsigned int s_hist[SEL_BINS];
+  for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) s_hist[i] = 0u;
   {
     const double* g = reinterpret_cast<const double*>(xfs + t.edge);
     double* s = reinterpret_cast<double*>(&sx);
@@ -119,10 +124,13 @@ knn_walk_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__
       const bool inlier = __dsqrt_rn(best) < thresh;
       corr[e.off + orig] = inlier ? bi : ~bi;
       d2out[e.off + orig] = best;
+      if (inlier) atomicAdd(&s_hist[(unsigned int)((unsigned long long)__double_as_longlong(best) >> 53)], 1u);   // select_hist_kernel, shift 53
     }
     __syncthreads();
     n_work = s_nfail;
   }
+  unsigned int* h = hist + (size_t)t.edge * SEL_BINS;
+  for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) if (s_hist[i]) atomicAdd(&h[i], s_hist[i]);
 }
 
 }  // namespace mv
