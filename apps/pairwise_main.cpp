@@ -1,8 +1,8 @@
 // apps/pairwise_main.cpp -- headless drop-in for the reference's `pairwise` executable (src/main_pairwise.cpp:29-134): a
 // cloud is moved by a known transform P and every pairwise solver has to recover P from the 1:1 correspondences; prints
 // the CPUTimer lines and the "Accurracy" block (translation / rotation error, common.h:259-282).  Reproduced: the three
-// Ceres-backed solvers (angle-axis, Eigen quaternion, Sophus SE3) on the GPU engine, point-to-point or --pointToPlane, and the
-// closed-form comparison row on the host (apps/closed_form.hpp).  Not reproduced: the g2o row (out of
+// Ceres-backed solvers (angle-axis, Eigen quaternion, Sophus SE3), point-to-point or --pointToPlane, and the closed-form
+// comparison row (mvicp_pairwise_closed).  Not reproduced: the g2o row (out of
 // scope) and addNoise's RNG stream -- the
 // perturbation of P comes from a fixed LCG with the same sigmas (0.1 rad, 0.1 m; main_pairwise.cpp:56).
 #include <chrono>
@@ -14,7 +14,6 @@
 #include <map>
 #include <string>
 #include "../compat/mvicp_compat.hpp"
-#include "closed_form.hpp"
 #include "io.hpp"
 
 typedef Eigen::Isometry3d Iso;
@@ -71,13 +70,13 @@ int main(int argc, char** argv) {
 
   std::map<std::string, float> timings;
   Iso closed;
-  {
+  try {
     const auto t0 = std::chrono::steady_clock::now();
-    closed = pointToPlane ? closed_form::pointToPlane(pts, dst, dnor) : closed_form::pointToPoint(pts, dst);   // main_pairwise.cpp:73,95
+    mvicp_compat::closedForm(pointToPlane, pts, dst, pointToPlane ? &dnor : nullptr, closed.data());   // main_pairwise.cpp:73,95
     const double s = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() * 1e-6;
     std::cout << std::endl << "=====  TIMING[closed] is " << s << " s" << std::endl << std::endl;
     timings["closed"] = (float)s;
-  }
+  } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 2; }
   const char* names[3] = {"ceres CeresAngleAxis", "ceres EigenQuaternion", "ceres SophusSE3"};
   const int params[3] = {MVICP_PARAM_AA, MVICP_PARAM_QUAT, MVICP_PARAM_SE3};
   Iso est[3];
@@ -89,11 +88,7 @@ int main(int argc, char** argv) {
       std::cout << std::endl << "=====  TIMING[" << names[k] << "] is " << s << " s" << std::endl << std::endl;   // CPUTimer.cpp:17-27
       timings[names[k]] = (float)s;
     }
-  } catch (const std::exception& e) {
-    std::cerr << e.what() << std::endl;
-    std::cout << "closed form      " << pose_diff(P, closed) << std::endl;
-    return 2;
-  }
+  } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 2; }
   std::cout << "=====  TIMINGS ====" << std::endl;                                                               // CPUTimer.cpp:28-36
   for (auto& kv : timings) { std::cout << std::left << std::setw(20) << kv.first << ":\t"; std::printf("%0.3f\n", kv.second); std::fflush(stdout); }
   std::cout << std::endl << "=====  Accurracy ====" << std::endl;

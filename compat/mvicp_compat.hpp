@@ -132,4 +132,12 @@ void pairwise(int param, bool pointToPlane, const std::vector<Vec3>& src, const 
                        nor ? (*nor)[0].data() : nullptr, (int64_t)src.size(), nullptr, pose16_out, nullptr));
 }
 
+// ICP_Closedform::pointToPoint / pointToPlane (include/icp-closedform.h; icp-closedform.cpp:9-54).
+template <class Vec3>
+void closedForm(bool pointToPlane, const std::vector<Vec3>& src, const std::vector<Vec3>& dst, const std::vector<Vec3>* nor, double pose16_out[16]) {
+  mvicp_config cfg{0, 0, nullptr};
+  check(mvicp_pairwise_closed(&cfg, pointToPlane ? MVICP_COST_P2PLANE : MVICP_COST_P2P, src[0].data(), dst[0].data(),
+                              nor ? (*nor)[0].data() : nullptr, (int64_t)src.size(), pose16_out));
+}
+
 }  // namespace mvicp_compat

@@ -144,6 +144,12 @@ int mvicp_pairwise(const mvicp_config* cfg, int32_t param, int32_t cost, const d
                    const double* nor_xyz, int64_t n, const mvicp_lm_options* opt, double* pose16_out,
                    mvicp_lm_summary* summary);
 
+/* ICP_Closedform::pointToPoint (cost = MVICP_COST_P2P: SVD of the centred cross-covariance, with the reference's
+ * `R.col(2) *= -1` for det < 0) / pointToPlane (MVICP_COST_P2PLANE: small-angle 6x6 normal equations, LDL^T, Rx Ry Rz)
+ * (src/internal/icp-closedform.cpp:9-54): the comparison baseline of main_pairwise.cpp:73,95 and a one-shot initialiser. */
+int mvicp_pairwise_closed(const mvicp_config* cfg, int32_t cost, const double* src_xyz, const double* dst_xyz, const double* nor_xyz,
+                          int64_t n, double* pose16_out);
+
 /* Frame::recomputeNormals for every frame (frame.cpp:244-255; default-on in main_multiview.cpp:49,68): k nearest
  * neighbours of each point in its own cloud (the point included; the reference uses k = 10) + pointSetPCA
  * (common.h:331-346).  The new normals replace the uploaded ones for mvicp_optimize; mvicp_get_normals copies them back

@@ -285,6 +285,16 @@ class ICP_Ceres:
         return out.reshape(4, 4).T.copy(), s.asdict()
 
     @staticmethod
+    def closed_form(src, dst, nor=None, device=0):
+        """ICP_Closedform::pointToPoint (nor is None) / pointToPlane (icp-closedform.cpp:9-54): 4x4 src -> dst."""
+        src = _f64(src).reshape(-1, 3); dst = _f64(dst).reshape(-1, 3)
+        nr = None if nor is None else _f64(nor).reshape(-1, 3)
+        out = np.zeros(16); cfg = Config(device, 0, None)
+        check(_lib.lib().mvicp_pairwise_closed(C.byref(cfg), C.c_int32(COST_P2P if nr is None else COST_P2PLANE), _p(src), _p(dst),
+                                               _p(nr) if nr is not None else None, C.c_int64(len(src)), _p(out)))
+        return out.reshape(4, 4).T.copy()
+
+    @staticmethod
     def pointToPoint_EigenQuaternion(src, dst, **kw): return ICP_Ceres._pairwise(PARAM_QUAT, COST_P2P, src, dst, **kw)
     @staticmethod
     def pointToPoint_CeresAngleAxis(src, dst, **kw): return ICP_Ceres._pairwise(PARAM_AA, COST_P2P, src, dst, **kw)

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/mvicp.h"
+#include "closed.cuh"
 #include "knn.cuh"
 #include "lm_eval.cuh"
 #include "lm_step.cuh"
@@ -872,6 +873,95 @@ int mvicp_pairwise(const mvicp_config* cfg, int32_t param, int32_t cost, const d
   mvicp_destroy(c);
   g_err = keep;
   return rc;
+}
+
+// ---- closed-form pairwise solvers (icp-closedform.cpp:9-54) ------------------------------
+static void host_eig_sym3(double A[3][3], double w[3], double V[3][3]) {   // cyclic Jacobi: A = V diag(w) V^T
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j);
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    if (A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2] < 1e-300) break;
+    for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+      if (A[p][q] == 0.0) continue;
+      const double th = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0)), cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+      for (int k = 0; k < 3; ++k) { const double a = A[k][p], b = A[k][q]; A[k][p] = cs * a - sn * b; A[k][q] = sn * a + cs * b; }
+      for (int k = 0; k < 3; ++k) { const double a = A[p][k], b = A[q][k]; A[p][k] = cs * a - sn * b; A[q][k] = sn * a + cs * b; }
+      for (int k = 0; k < 3; ++k) { const double a = V[k][p], b = V[k][q]; V[k][p] = cs * a - sn * b; V[k][q] = sn * a + cs * b; }
+    }
+  }
+  for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+int mvicp_pairwise_closed(const mvicp_config* cfg, int32_t cost, const double* src, const double* dst, const double* nor, int64_t n,
+                          double* pose16_out) {
+  if (!src || !dst || n <= 0 || !pose16_out) return fail(MVICP_ERR_INVALID, "mvicp_pairwise_closed: bad arguments");
+  if (cost != MVICP_COST_P2P && cost != MVICP_COST_P2PLANE) return fail(MVICP_ERR_INVALID, "mvicp_pairwise_closed: cost must be P2P or P2PLANE");
+  if (cost == MVICP_COST_P2PLANE && !nor) return fail(MVICP_ERR_INVALID, "mvicp_pairwise_closed: point-to-plane needs dst normals");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(MVICP_ERR_CUDA, "no CUDA device; this engine has no CPU path");
+  const int dev = cfg ? cfg->device : 0;
+  if (dev < 0 || dev >= ndev) return fail(MVICP_ERR_INVALID, "mvicp_pairwise_closed: bad device %d", dev);
+  CU(cudaSetDevice(dev));
+  cudaStream_t st = cfg && cfg->stream ? (cudaStream_t)cfg->stream : nullptr;
+  const size_t bytes = sizeof(double) * 3 * (size_t)n;
+  const int grid = (int)std::min<int64_t>(2 * 148, (n + CLOSED_THREADS - 1) / CLOSED_THREADS);
+  double *d_src = nullptr, *d_dst = nullptr, *d_nor = nullptr, *d_part = nullptr, *d_aux = nullptr;
+  std::vector<double> part((size_t)grid * CLOSED_MAXV);
+  auto cleanup = [&]() { cudaFree(d_src); cudaFree(d_dst); cudaFree(d_nor); cudaFree(d_part); cudaFree(d_aux); };
+#define CUX(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return fail(MVICP_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  CUX(cudaMalloc(&d_src, bytes)); CUX(cudaMalloc(&d_dst, bytes)); CUX(cudaMalloc(&d_part, sizeof(double) * part.size())); CUX(cudaMalloc(&d_aux, sizeof(double) * 6));
+  CUX(cudaMemcpyAsync(d_src, src, bytes, cudaMemcpyHostToDevice, st)); CUX(cudaMemcpyAsync(d_dst, dst, bytes, cudaMemcpyHostToDevice, st));
+  if (cost == MVICP_COST_P2PLANE) { CUX(cudaMalloc(&d_nor, bytes)); CUX(cudaMemcpyAsync(d_nor, nor, bytes, cudaMemcpyHostToDevice, st)); }
+  auto fetch = [&](int nv, double* out) -> int {   // per-CTA partials, summed in CTA order
+    if (cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    for (int i = 0; i < nv; ++i) { double s = 0; for (int b = 0; b < grid; ++b) s += part[(size_t)b * CLOSED_MAXV + i]; out[i] = s; }
+    return 0;
+  };
+  for (int i = 0; i < 16; ++i) pose16_out[i] = 0.0;
+  pose16_out[15] = 1.0;
+  if (cost == MVICP_COST_P2P) {
+    double sums[6], K9[9];
+    closed_reduce_kernel<0><<<grid, CLOSED_THREADS, 0, st>>>(d_src, d_dst, nullptr, (long long)n, nullptr, d_part);
+    if (fetch(6, sums)) { cleanup(); return fail(MVICP_ERR_CUDA, "mvicp_pairwise_closed: reduction failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    for (int i = 0; i < 6; ++i) sums[i] /= (double)n;            // pbar, qbar
+    CUX(cudaMemcpyAsync(d_aux, sums, sizeof sums, cudaMemcpyHostToDevice, st));
+    closed_reduce_kernel<1><<<grid, CLOSED_THREADS, 0, st>>>(d_src, d_dst, nullptr, (long long)n, d_aux, d_part);
+    if (fetch(9, K9)) { cleanup(); return fail(MVICP_ERR_CUDA, "mvicp_pairwise_closed: reduction failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    // R = U V^T of K (its orthogonal polar factor) = K V diag(1/sigma) V^T with K^T K = V diag(sigma^2) V^T; the reference's
+    // `R.col(2) *= -1` when det R < 0 (icp-closedform.cpp:20-22); t = qbar - R pbar
+    double S[3][3], w[3], V[3][3], R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { S[a][b] = 0; for (int k = 0; k < 3; ++k) S[a][b] += K9[3 * k + a] * K9[3 * k + b]; }
+    host_eig_sym3(S, w, V);
+    for (int j = 0; j < 3; ++j) {
+      const double sg = std::sqrt(w[j] > 0 ? w[j] : 0.0);
+      for (int a = 0; a < 3; ++a) { double u = 0; for (int k = 0; k < 3; ++k) u += K9[3 * a + k] * V[k][j]; u /= sg; for (int b = 0; b < 3; ++b) R[a][b] += u * V[b][j]; }
+    }
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) + R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    if (det < 0) for (int a = 0; a < 3; ++a) R[a][2] = -R[a][2];
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) pose16_out[4 * b + a] = R[a][b];
+      pose16_out[12 + a] = sums[3 + a] - (R[a][0] * sums[0] + R[a][1] * sums[1] + R[a][2] * sums[2]);
+    }
+  } else {
+    double v[27];
+    closed_reduce_kernel<2><<<grid, CLOSED_THREADS, 0, st>>>(d_src, d_dst, d_nor, (long long)n, nullptr, d_part);
+    if (fetch(27, v)) { cleanup(); return fail(MVICP_ERR_CUDA, "mvicp_pairwise_closed: reduction failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    double Cm[6][6], L[6][6] = {{0}}, D[6], y[6], x[6];
+    { int k = 0; for (int r = 0; r < 6; ++r) for (int c2 = r; c2 < 6; ++c2) { Cm[r][c2] = v[k]; Cm[c2][r] = v[k]; ++k; } }
+    for (int j = 0; j < 6; ++j) {      // LDL^T (icp-closedform.cpp:46)
+      double dj = Cm[j][j]; for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k] * D[k];
+      D[j] = dj; L[j][j] = 1;
+      for (int i = j + 1; i < 6; ++i) { double u = Cm[i][j]; for (int k = 0; k < j; ++k) u -= L[i][k] * L[j][k] * D[k]; L[i][j] = u / dj; }
+    }
+    for (int i = 0; i < 6; ++i) { y[i] = v[21 + i]; for (int k = 0; k < i; ++k) y[i] -= L[i][k] * y[k]; }
+    for (int i = 5; i >= 0; --i) { x[i] = y[i] / D[i]; for (int k = i + 1; k < 6; ++k) x[i] -= L[k][i] * x[k]; }
+    const double ca = std::cos(x[0]), sa = std::sin(x[0]), cb = std::cos(x[1]), sb = std::sin(x[1]), cg = std::cos(x[2]), sg = std::sin(x[2]);
+    const double R[3][3] = {{cb * cg, -cb * sg, sb}, {sa * sb * cg + ca * sg, -sa * sb * sg + ca * cg, -sa * cb}, {-ca * sb * cg + sa * sg, ca * sb * sg + sa * cg, ca * cb}};
+    for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) pose16_out[4 * b + a] = R[a][b]; pose16_out[12 + a] = x[3 + a]; }   // Rx Ry Rz, t (:48-52)
+  }
+#undef CUX
+  cleanup();
+  return MVICP_OK;
 }
 
 // ---- normal estimation ---------------------------------------------------------------

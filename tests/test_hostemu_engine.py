@@ -188,3 +188,13 @@ def test_graph_walk_is_bit_identical(emu, oracle, golden_dir):
     for r0, r1 in zip(*res):
         for (i0, d0), (i1, d1) in zip(r0, r1):
             assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
+
+
+def test_closed_form_pairwise(emu, oracle):
+    import test_gpu_zz_closed_form as T
+    for n in (1, 3, 300, 20011):
+        T.test_point_to_point_matches_oracle(oracle, n)
+    T.test_reflection_branch_follows_the_reference(oracle)
+    for n in (300, 20011):
+        T.test_point_to_plane_matches_oracle(oracle, n)
+    T.test_arguments()
