@@ -198,3 +198,28 @@ def test_closed_form_pairwise(emu, oracle):
     for n in (300, 20011):
         T.test_point_to_plane_matches_oracle(oracle, n)
     T.test_arguments()
+
+
+def test_every_kernel_family_under_address_sanitizer(tmp_path):
+    """tools/sanitize_run.py (every kernel family, both storage modes, general path, 40 views, experimental schedules) + the
+    closed forms on an AddressSanitizer build of the emulated engine: device buffers are heap blocks there, so an out-of-bounds
+    access by a kernel aborts the run (the CPU counterpart of profiles/r1_sanitizer.txt's memcheck)."""
+    import subprocess
+    import build_hostemu
+    so = build_hostemu.build(asan=True)
+    asan = subprocess.run(["/usr/bin/g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    script = tmp_path / "run.py"
+    script.write_text(f"""
+import sys, ctypes as C, runpy
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+from mv_lm_icp_b200 import _lib, ICP_Ceres
+lib = C.CDLL({so!r}); lib.mvicp_last_error.restype = C.c_char_p; _lib._lib = lib
+runpy.run_path({os.path.join(ROOT, 'tools', 'sanitize_run.py')!r}, run_name='__main__')
+from helpers import scene
+sc = scene(2, 3001, 13)
+ICP_Ceres.closed_form(sc['pts'][0], sc['pts'][0] + 0.01); ICP_Ceres.closed_form(sc['pts'][0], sc['pts'][0] + 0.01, sc['nor'][0])
+print('ASAN RUN DONE')
+""")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=1200, env=env)
+    assert r.returncode == 0 and "ASAN RUN DONE" in r.stdout and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
