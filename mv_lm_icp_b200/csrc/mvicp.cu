@@ -19,6 +19,7 @@
 
 #include "../../include/mvicp.h"
 #include "closed.cuh"
+#include "far.cuh"
 #include "knn.cuh"
 #include "lm_eval.cuh"
 #include "lm_step.cuh"
@@ -79,6 +80,9 @@ struct mvicp_ctx {
   std::vector<void*> frame_allocs;
   DevBuf d_walk;               // WalkDev per frame (MVICP_FLAG_GRAPH_WALK only)
   bool walk_ready = false;
+  DevBuf d_obb;                // ObbDev per frame (MVICP_FLAG_OBB_FAR only)
+  bool obb_ready = false;
+  int last_lm_iters = 1 << 20; // LM iterations of the previous mvicp_optimize: large = the clouds are still far apart
   DevBuf d_frames, d_poses;
   std::vector<uint8_t> fixed;
   std::vector<double> h_poses;   // mirror of the last set/get (pose graph construction is host side)
@@ -214,7 +218,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_walk};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_walk, &c->d_obb};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -297,6 +301,28 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
   CU(cudaMemcpy(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * M, cudaMemcpyHostToDevice));
   c->fixed.assign(M, 0); c->fixed[0] = 1;
   c->E = 0; c->h_edges.clear(); c->have_corr = false;
+  c->obb_ready = false; c->last_lm_iters = 1 << 20;
+  if (c->flags & MVICP_FLAG_OBB_FAR) {      // experimental: hybrid oriented boxes for the far rounds (far.cuh)
+    std::vector<ObbDev> ho(M);
+    std::vector<std::vector<ObbHost>> obbs(M);
+    {
+      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      std::vector<std::thread> pool; std::atomic<int> next{0};
+      for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)M); ++t)
+        pool.emplace_back([&]() { for (int f; (f = next.fetch_add(1)) < M;) build_obb(pts[f], n_pts[f], builds[f], obbs[f]); });
+      for (auto& th : pool) th.join();
+    }
+    static_assert(sizeof(ObbHost) == sizeof(ObbNode) && sizeof(ObbNode) == 64, "oriented node = 64 bytes");
+    for (int f = 0; f < M; ++f) {
+      void* d = nullptr;
+      CU(cudaMalloc(&d, sizeof(ObbNode) * obbs[f].size())); c->frame_allocs.push_back(d);
+      CU(cudaMemcpy(d, obbs[f].data(), sizeof(ObbNode) * obbs[f].size(), cudaMemcpyHostToDevice));
+      ho[f] = ObbDev{(const ObbNode*)d};
+    }
+    RET(c->d_obb.reserve(sizeof(ObbDev) * M));
+    CU(cudaMemcpy(c->d_obb.p, ho.data(), sizeof(ObbDev) * M, cudaMemcpyHostToDevice));
+    c->obb_ready = true;
+  }
   c->walk_ready = false;
   if (c->flags & MVICP_FLAG_GRAPH_WALK) {   // experimental: neighbour lists + certificate radii of every cloud (walk.cuh)
     std::vector<WalkDev> hw(M);
@@ -458,7 +484,13 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
   bool hist0_done = false;   // the walk kernel delivers the select's first histogram itself
   if (c->n_knn_tiles) {
-    if (seed && c->walk_ready) {   // experimental: neighbour-graph walk with certificate, tree search as fallback (walk.cuh)
+    // experimental far-round kernel: no seeds yet, or the previous LM solve still needed several iterations (far.cuh)
+    const bool far = c->obb_ready && (!seed || c->last_lm_iters >= 4);
+    if (far) {
+      knn_far_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
+          c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
+          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh, c->d_obb.as<ObbDev>());
+    } else if (seed && c->walk_ready) {   // experimental: neighbour-graph walk with certificate, tree search as fallback (walk.cuh)
       knn_walk_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
           c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
           c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, c->d_walk.as<WalkDev>(),
@@ -832,6 +864,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   std::memcpy(&st, c->h_state, sizeof st);
   CU(cudaGetLastError());
   c->ev_lm = true;
+  c->last_lm_iters = st.iteration;
   if (summary) {
     summary->termination = st.termination; summary->num_iterations = st.iteration; summary->num_successful_steps = st.n_success;
     summary->num_evaluations = st.n_evals; summary->num_linear_solves = st.n_solves; summary->reserved = 0;

@@ -7,7 +7,7 @@ import pytest
 
 from helpers import oracle_correspond, scene
 from mv_lm_icp_b200 import Engine, synth
-from mv_lm_icp_b200.api import FLAG_GRAPH_WALK, FLAG_NO_SEED, FLAG_WARP_SEARCH
+from mv_lm_icp_b200.api import FLAG_GRAPH_WALK, FLAG_NO_SEED, FLAG_OBB_FAR, FLAG_WARP_SEARCH
 
 pytestmark = pytest.mark.gpu
 
@@ -47,9 +47,10 @@ def test_synthetic_bit_exact(oracle, n_views, n_points, cfg):
     eng.close()
 
 
-# MVICP_FLAG_GRAPH_WALK has not run on a GPU yet (written after the round's GPU budget was spent; its logic is covered on
+# MVICP_FLAG_GRAPH_WALK and MVICP_FLAG_OBB_FAR have not run on a GPU yet (written after the round's GPU budget was spent; its logic is covered on
 # the host model, tests/test_hostemu_engine.py): the GPU suite includes it only on request.
-EXPERIMENTAL = (FLAG_GRAPH_WALK, FLAG_GRAPH_WALK | FLAG_WARP_SEARCH) if os.environ.get("MVICP_TEST_EXPERIMENTAL") else ()
+EXPERIMENTAL = ((FLAG_GRAPH_WALK, FLAG_GRAPH_WALK | FLAG_WARP_SEARCH, FLAG_OBB_FAR, FLAG_OBB_FAR | FLAG_NO_SEED, FLAG_OBB_FAR | FLAG_GRAPH_WALK)
+                if os.environ.get("MVICP_TEST_EXPERIMENTAL") else ())
 
 
 def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=EXPERIMENTAL):

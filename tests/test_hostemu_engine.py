@@ -50,7 +50,8 @@ def test_exports_every_abi_symbol(emu):
 def test_correspondence_step(emu, oracle, golden_dir):
     import test_gpu_corr as T
     T.test_synthetic_bit_exact(oracle, 4, 5000, 21)
-    T.test_seed_and_schedule_do_not_change_results(oracle, extra_flags=(T.FLAG_GRAPH_WALK, T.FLAG_GRAPH_WALK | T.FLAG_WARP_SEARCH))
+    T.test_seed_and_schedule_do_not_change_results(oracle, extra_flags=(T.FLAG_GRAPH_WALK, T.FLAG_GRAPH_WALK | T.FLAG_WARP_SEARCH, T.FLAG_OBB_FAR,
+                                                                        T.FLAG_OBB_FAR | T.FLAG_NO_SEED, T.FLAG_OBB_FAR | T.FLAG_GRAPH_WALK))
     T.test_real_bunny_pair_fp64_storage(oracle, golden_dir)
     T.test_real_dinosaur_pair_mm_units(golden_dir)
     T.test_edge_cases(oracle)
@@ -138,14 +139,16 @@ def test_headless_driver_on_the_emulated_engine(emu, tmp_path):
         assert len(m) == 4 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m[1:])
 
 
-def test_graph_walk_is_bit_identical(emu, oracle, golden_dir):
-    """MVICP_FLAG_GRAPH_WALK (csrc/walk.cuh, experimental): seeded rounds answer most queries by a certified walk on the dst
-    cloud's neighbour graph.  Same matches, same distances, same poses as the default search -- over ICP rounds that go
+@pytest.mark.parametrize("xflags", [8, 16, 24], ids=["graph-walk", "obb-far", "both"])
+def test_experimental_schedules_are_bit_identical(emu, oracle, golden_dir, xflags):
+    """MVICP_FLAG_GRAPH_WALK (csrc/walk.cuh): seeded rounds answer most queries by a certified walk on the dst cloud's
+    neighbour graph; MVICP_FLAG_OBB_FAR (csrc/far.cuh): far rounds search a second tree of hybrid oriented boxes.  Same
+    matches, same distances, same poses as the default search -- over ICP rounds that go
     from far (certificates fail, tree fallback) to converged (certificates hold), on fp32 and fp64 storage, with exact
     duplicates and with clouds too small to have neighbour lists."""
     from helpers import scene
     from mv_lm_icp_b200 import Engine, synth
-    from mv_lm_icp_b200.api import FLAG_GRAPH_WALK
+    FLAG_GRAPH_WALK = xflags
     sc = scene(4, 3001, 27)
     edges = synth.ring_edges(4, 2)
     runs = []

@@ -52,7 +52,7 @@ def one(seed):
         poses.append(P)
     edges = [(s, d) for s in range(M) for d in range(M) if s != d and rng.integers(0, 2)] or [(1, 0)]
     thresh = float(rng.choice([0.05, 0.5, 5.0])) * scale
-    flags = int(rng.choice([0, 1, 4, 8, 12]))
+    flags = int(rng.choice([0, 1, 4, 8, 12, 16, 17, 24]))
     eng = Engine(flags=flags); eng.set_frames(pts, None); eng.set_graph(edges)
     fixed = [1] + [0] * (M - 1)
     for rnd in range(3):

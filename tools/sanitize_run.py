@@ -7,11 +7,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mv_lm_icp_b200 as mv
 from mv_lm_icp_b200 import synth
-from mv_lm_icp_b200.api import FLAG_GRAPH_WALK, FLAG_WARP_SEARCH, ICP_Ceres
+from mv_lm_icp_b200.api import FLAG_GRAPH_WALK, FLAG_OBB_FAR, FLAG_WARP_SEARCH, ICP_Ceres
 
 sc = synth.make_scene(4, 1501, config_id=1)
 edges = synth.ring_edges(4, 2)
-for flags in (0, FLAG_WARP_SEARCH, FLAG_GRAPH_WALK):
+for flags in (0, FLAG_WARP_SEARCH, FLAG_GRAPH_WALK, FLAG_OBB_FAR | FLAG_GRAPH_WALK):
     eng = mv.Engine(device=0, flags=flags)
     eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
     for param in (mv.PARAM_SE3, mv.PARAM_QUAT, mv.PARAM_AA):
