@@ -335,6 +335,7 @@ def run_ours(args, cfg):
                           "lm_iterations_per_round": [p["lm_iters"] for p in per],
                           "per_round_ms": [round(p["ms"], 3) for p in per],
                           "per_rank_ms_per_step": per_rank,
+                          "engine_flags": args.flags,
                           "storage": "fp32 records (lossless), fp64 arithmetic"},
                "e2e": {"value": 1e3 / (e2e_ms / K), "unit": "iter/s", "h2d_bytes_per_step": pose_bytes, "d2h_bytes_per_step": pose_bytes,
                        "note": "per step: poses host->device, correspond+optimize, poses device->host through the C ABI; clouds uploaded once "
