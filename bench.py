@@ -179,7 +179,7 @@ def run_reference(args, cfg):
     scale = E_full / E_sub
     per_round = float(np.mean([a + b for a, b, _ in timed])) * scale
     val = 1.0 / per_round
-    sample = (f"rounds 0..{args.steps - 1} (after a warm-up round) of the sub-problem views 0..{views_sub - 1} ({E_sub} of {E_full} directed "
+    sample = (f"rounds 0..{args.steps - 1} ({'after a warm-up round' if args.warmup > 0 else 'no warm-up'}) of the sub-problem views 0..{views_sub - 1} ({E_sub} of {E_full} directed "
               f"edges, {cfg['points']} queries each), extrapolated x{scale:.2f} by edge count; NN = "
               f"{'reference nanoflann.hpp (oracle/_ref)' if kind == 'ref' else 'oracle KD-tree port'}, LM = oracle port of the "
               f"Ceres path (Jet autodiff, dense Cholesky; Ceres not installable), {threads} OpenMP threads; index build excluded")
