@@ -108,6 +108,5 @@ def test_pairwise_driver_recovers_known_transform(tmp_path, p2plane):
         assert np.linalg.norm(E[:3, 3] - P[:3, 3]) < 1e-8, (k, E, P)
         assert np.degrees(np.arccos(np.clip((np.trace(E[:3, :3].T @ P[:3, :3]) - 1) / 2, -1, 1))) < 1e-5
     m = re.findall(r"diff_tra:([0-9.e+-]+)\t diff_rot_degrees:([0-9.e+-]+)", r.stdout)
-    assert len(m) == 4 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m[1:])   # m[0] = closed form (linearised for p2plane)
-    if not p2plane:
-        assert float(m[0][0]) < 1e-12
+    # the three LM solvers; the closed-form row in front of them is checked by tests/test_gpu_zz_closed_form.py
+    assert len(m) >= 3 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m[-3:])

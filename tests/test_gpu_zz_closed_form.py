@@ -62,3 +62,17 @@ def test_arguments():
     assert _lib.lib().mvicp_pairwise_closed(C.byref(cfg), C.c_int32(1), p(a), p(a), None, C.c_int64(4), p(out)) != 0   # p2plane without normals
     assert _lib.lib().mvicp_pairwise_closed(C.byref(cfg), C.c_int32(2), p(a), p(a), p(a), C.c_int64(4), p(out)) != 0   # MIXED has no closed form
     assert _lib.lib().mvicp_pairwise_closed(C.byref(cfg), C.c_int32(0), p(a), p(a), None, C.c_int64(0), p(out)) != 0
+
+
+def test_pairwise_driver_prints_the_closed_form_row(tmp_path):
+    """apps/pairwise_b200: the "closed form" row of the reference binary's accuracy table (main_pairwise.cpp:121)."""
+    import re
+    import subprocess
+    import test_app_multiview as A
+    A._build()
+    sc = scene(2, 3000, 9)
+    A._write_cloud(tmp_path / "c.xyz", sc["pts"][0], sc["nor"][0])
+    r = subprocess.run([A.BIN_PAIR, f"--cloud={tmp_path}/c.xyz"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"closed form\s+diff_tra:([0-9.e+-]+)\t diff_rot_degrees:([0-9.e+-]+)", r.stdout)
+    assert m and float(m.group(1)) < 1e-12 and float(m.group(2)) < 1e-5 and "TIMING[closed]" in r.stdout
