@@ -80,6 +80,8 @@ struct mvicp_ctx {
   std::vector<void*> frame_allocs;
   DevBuf d_walk;               // WalkDev per frame (MVICP_FLAG_GRAPH_WALK only)
   bool walk_ready = false;
+  DevBuf d_guess, d_gcand;     // median brackets per edge + their candidate keys (walk.cuh)
+  bool guess_armed = false;
   DevBuf d_obb;                // ObbDev per frame (MVICP_FLAG_OBB_FAR only)
   bool obb_ready = false;
   int last_lm_iters = 1 << 20; // LM iterations of the previous mvicp_optimize: large = the clouds are still far apart
@@ -218,7 +220,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_walk, &c->d_obb};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_walk, &c->d_obb, &c->d_guess, &c->d_gcand};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -355,6 +357,8 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
 int mvicp_set_poses(mvicp_ctx* c, const double* poses16, const uint8_t* fixed) {
   if (!c || !c->M || !poses16) return fail(MVICP_ERR_INVALID, "mvicp_set_poses: bad arguments / no frames");
   CU(cudaSetDevice(c->device));
+  // poses other than the ones this context last handed out: what the previous LM solve said about convergence is void
+  if (std::memcmp(c->h_poses.data(), poses16, sizeof(double) * 16 * c->M) != 0) c->last_lm_iters = 1 << 20;
   std::memcpy(c->h_poses.data(), poses16, sizeof(double) * 16 * c->M);
   CU(cudaMemcpyAsync(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * c->M, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -420,6 +424,8 @@ static int rebuild_work(mvicp_ctx* c) {
   RET(c->d_median.reserve(sizeof(double) * E));
   RET(c->d_selcand.reserve(sizeof(unsigned long long) * SEL_CAP * (size_t)E));
   RET(c->d_selcand_n.reserve(sizeof(unsigned int) * E));
+  if (c->flags & MVICP_FLAG_GRAPH_WALK) { RET(c->d_guess.reserve(sizeof(SelGuess) * E)); RET(c->d_gcand.reserve(sizeof(unsigned long long) * GUESS_CAP * (size_t)E)); }
+  c->guess_armed = false;
   RET(c->d_knn_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, kt.size())));
   RET(c->d_eval_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, et.size())));
   RET(c->d_edge_tile_begin.reserve(sizeof(int32_t) * (E + 1)));
@@ -483,6 +489,9 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
   bool hist0_done = false;   // the walk kernel delivers the select's first histogram itself
+  // converged rounds (the previous LM solve took one iteration: poses unchanged up to conversion rounding): the walk kernel
+  // also brackets the median, and one small kernel per edge replaces the whole select (walk.cuh)
+  const bool use_guess = seed && c->walk_ready && c->guess_armed && c->last_lm_iters <= 1;
   if (c->n_knn_tiles) {
     // experimental far-round kernel: no seeds yet, or the previous LM solve still needed several iterations (far.cuh)
     const bool far = c->obb_ready && (!seed || c->last_lm_iters >= 4);
@@ -494,7 +503,8 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
       knn_walk_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
           c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
           c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, c->d_walk.as<WalkDev>(),
-          c->d_hist.as<unsigned int>());
+          use_guess ? nullptr : c->d_hist.as<unsigned int>(), use_guess ? c->d_guess.as<SelGuess>() : nullptr,
+          c->d_gcand.as<unsigned long long>());
       hist0_done = true;
     } else {
       auto kern = (c->flags & MVICP_FLAG_WARP_SEARCH) ? knn_kernel<F32, true> : knn_kernel<F32, false>;
@@ -505,6 +515,15 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   }
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);
+  if (use_guess && hist0_done) {
+    select_guess_finish_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
+                                                               c->d_sel.as<SelState>(), c->d_guess.as<SelGuess>(), c->d_gcand.as<unsigned long long>(),
+                                                               c->d_weight.as<float>(), c->d_median.as<double>(), c->d_count.as<unsigned long long>());
+    c->stats.kernel_launches += 1;
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    CU(cudaGetLastError());
+    return MVICP_OK;
+  }
   // exact median -> weight
   select_init_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_sel.as<SelState>(), E);
   c->stats.kernel_launches += 1;
@@ -528,6 +547,11 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
                                                          c->d_sel.as<SelState>(), c->d_selcand.as<unsigned long long>(),
                                                          c->d_selcand_n.as<unsigned int>(), c->d_weight.as<float>(), c->d_median.as<double>());
   c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
+  if (c->walk_ready) {   // bracket the exact median for a later converged round
+    select_guess_arm_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_guess.as<SelGuess>(), E);
+    c->stats.kernel_launches += 1;
+    c->guess_armed = true;
+  }
   CU(cudaEventRecord(c->ev[2], c->stream));
   CU(cudaGetLastError());
   return MVICP_OK;

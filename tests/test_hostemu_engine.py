@@ -227,3 +227,27 @@ print('ASAN RUN DONE')
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=1200, env=env)
     assert r.returncode == 0 and "ASAN RUN DONE" in r.stdout and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
+
+
+def test_median_bracket_replaces_the_select_in_converged_rounds(emu, oracle):
+    """With MVICP_FLAG_GRAPH_WALK, a round that follows a one-iteration LM solve brackets the median inside the NN kernel and
+    finishes it with one small kernel per edge (walk.cuh): fewer launches, the same weights, counts and poses bit for bit."""
+    _first_pass_only(emu)
+    from helpers import scene
+    from mv_lm_icp_b200 import Engine, synth
+    sc = scene(4, 12000, 3)
+    edges = synth.ring_edges(4, 2)
+    runs = []
+    for flags in (0, 8):
+        eng = Engine(flags=flags); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_gt"])
+        out = []; l0 = eng.stats()["kernel_launches"]
+        for rnd in range(10):
+            s = eng.icp_round(0.005, 2, 1, True); l1 = eng.stats()["kernel_launches"]
+            out.append((s["num_iterations"], eng.get_poses(), [eng.get_edge(e, arrays=False) for e in range(len(edges)) if edges[e][0] != 0], l1 - l0)); l0 = l1
+        runs.append(out); eng.close()
+    bracketed = 0
+    for (it0, P0, w0, n0), (it1, P1, w1, n1) in zip(*runs):
+        assert it0 == it1 and np.array_equal(P0.view(np.uint64), P1.view(np.uint64))
+        assert all(a[-2] == b[-2] and np.float32(a[-1]).view(np.uint32) == np.float32(b[-1]).view(np.uint32) for a, b in zip(w0, w1))
+        bracketed += int(n1 < n0)
+    assert bracketed >= 2 and runs[0][-1][0] == 1        # the scene converges to one-iteration solves; those rounds skip the select
