@@ -118,6 +118,18 @@ class Engine:
         c = cnt.value
         return first[:c].copy(), second[:c].copy(), dist[:c].copy(), np.float32(w.value)
 
+    def pull_all_edges(self):
+        """Every edge's (first, second, dist) list and weight into host arrays, as Frame::computeClosestPointsToNeighbours
+        leaves them in OutgoingEdge::correspondances (frame.cpp:158,176).  Returns the number of bytes that reached the host."""
+        nb = 0
+        self.host_edges = []
+        for e, (s, d) in enumerate(self.edges):
+            if s == 0:
+                self.host_edges.append(None); continue
+            f, sec, dist, w = self.get_edge(e)
+            self.host_edges.append((f, sec, dist, w)); nb += 16 * len(f) + 4
+        return nb
+
     def get_nn(self, e):
         n = self.n_pts[self.edges[e][0]]
         idx = np.empty(n, np.int32); d2 = np.empty(n, np.float64)
@@ -146,10 +158,15 @@ class Engine:
                                       C.c_int32(int(robust)), C.byref(options) if options is not None else None, C.byref(s)))
         return s.asdict()
 
-    def recompute_normals(self, k=10):
-        """Frame::recomputeNormals for every frame (frame.cpp:244-255). Returns (list of [N,3] normals, device ms)."""
+    def recompute_normals(self, k=10, fetch=True):
+        """Frame::recomputeNormals for every frame (frame.cpp:244-255). Returns (list of [N,3] normals, device ms);
+        fetch=False leaves the normals on the device (list is None)."""
         check(self._l.mvicp_recompute_normals(self._ctx, C.c_int32(k)))
         out = []; ms = C.c_float(0)
+        if not fetch:
+            nor = np.empty((self.n_pts[0], 3))
+            check(self._l.mvicp_get_normals(self._ctx, C.c_int32(0), _p(nor), C.byref(ms)))
+            return None, ms.value
         for f in range(self.M):
             nor = np.empty((self.n_pts[f], 3))
             check(self._l.mvicp_get_normals(self._ctx, C.c_int32(f), _p(nor), C.byref(ms)))

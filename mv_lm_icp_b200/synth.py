@@ -151,12 +151,12 @@ def make_view(v, n_views, n_points, seed, depth_sigma=5e-5, half_fov=0.30):
     return pts, nor, P
 
 
-def make_scene(n_views, n_points, config_id=3, sigma_rot=0.02, sigma_tra=0.01):
-    """Returns dict(pts, nor, poses_gt, poses_init); seeds 0xB200 + 1000*config + view."""
-    pts, nor, gt, init = [], [], [], []
+def scene_poses(n_views, config_id=3, sigma_rot=0.02, sigma_tra=0.01):
+    """Ground-truth ring poses and the seeded noisy initial poses of a scene (no ray casting): (gt[M,4,4], init[M,4,4])."""
+    gt, init = [], []
     for v in range(n_views):
-        p, n, P = make_view(v, n_views, n_points, 0xB200 + 1000 * config_id + v)
-        pts.append(p); nor.append(n); gt.append(P)
+        P = _camera_pose(2.0 * np.pi * v / n_views)
+        gt.append(P)
         if v == 0:
             init.append(P.copy())
         else:
@@ -165,7 +165,17 @@ def make_scene(n_views, n_points, config_id=3, sigma_rot=0.02, sigma_tra=0.01):
             Q[:3, :3] = P[:3, :3] @ _so3_exp(rng.normal(0.0, sigma_rot, 3))
             Q[:3, 3] = P[:3, 3] + rng.normal(0.0, sigma_tra, 3)
             init.append(Q)
-    return {"pts": pts, "nor": nor, "poses_gt": np.stack(gt), "poses_init": np.stack(init)}
+    return np.stack(gt), np.stack(init)
+
+
+def make_scene(n_views, n_points, config_id=3, sigma_rot=0.02, sigma_tra=0.01):
+    """Returns dict(pts, nor, poses_gt, poses_init); seeds 0xB200 + 1000*config + view."""
+    pts, nor = [], []
+    for v in range(n_views):
+        p, n, _ = make_view(v, n_views, n_points, 0xB200 + 1000 * config_id + v)
+        pts.append(p); nor.append(n)
+    gt, init = scene_poses(n_views, config_id, sigma_rot, sigma_tra)
+    return {"pts": pts, "nor": nor, "poses_gt": gt, "poses_init": init}
 
 
 def ring_edges(n_views, knn=2):

@@ -38,10 +38,11 @@ class LmSummary(C.Structure):
 def build(force=False):
     """Compile liboracle.so (+ _ref when /root/reference is present). Idempotent."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_icp.cpp", "geom.h", "jet.h", "lm.h", "ref_nanoflann.cpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_icp.cpp", "geom.h", "jet.h", "lm.h", "ref_nanoflann.cpp", "ref_functors.cpp", "Makefile")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     ref_so = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
-    if not os.path.exists(ref_so) and os.path.exists("/root/reference/include/nanoflann.hpp"):
+    fun_so = os.path.join(_HERE, "_ref", "libref_functors.so")
+    if (not os.path.exists(ref_so) or not os.path.exists(fun_so)) and os.path.exists("/root/reference/include/nanoflann.hpp"):
         stale = True
     if stale:
         subprocess.run(["make", "-C", _HERE, "-s", "all"], check=True, stdout=subprocess.DEVNULL)
@@ -73,6 +74,40 @@ def ref_lib():
         _ref = C.CDLL(p)
         _ref.ref_kd_build.restype = C.c_void_p
     return _ref
+
+
+_fun = None
+
+
+def ref_functors():
+    """The reference's own cost-functor text (include/icp-ceres.h, include/eigen_quaternion.h) compiled against oracle/stubs
+    (oracle/ref_functors.cpp); None if it was never built (no /root/reference at build time)."""
+    global _fun
+    if _fun is None:
+        build()
+        p = os.path.join(_HERE, "_ref", "libref_functors.so")
+        if not os.path.exists(p):
+            return None
+        _fun = C.CDLL(p)
+    return _fun
+
+
+def functor_eval(param, plane, cam1, cam2, src, dst, nor, which="oracle"):
+    """(residuals[NR], ambient Jacobian[NR, 2G]) of one multiview functor: which = 'oracle' (restatement) or 'ref' (reference text)."""
+    G = 6 if param == PARAM_AA else 7
+    nr = 1 if plane else 3
+    r = np.zeros(3); jac = np.zeros(3 * 2 * G)
+    fn = lib().orc_functor_eval if which == "oracle" else ref_functors().ref_functor_global
+    fn(C.c_int(param), C.c_int(int(plane)), _p(_f64(cam1)), _p(_f64(cam2)), _p(_f64(src)), _p(_f64(dst)), _p(_f64(nor)), _p(r), _p(jac))
+    return r[:nr].copy(), jac[:nr * 2 * G].reshape(nr, 2 * G).copy()
+
+
+def functor_eval_pairwise_ref(param, plane, cam, src, dst, nor):
+    G = 6 if param == PARAM_AA else 7
+    nr = 1 if plane else 3
+    r = np.zeros(3); jac = np.zeros(3 * G)
+    ref_functors().ref_functor_pairwise(C.c_int(param), C.c_int(int(plane)), _p(_f64(cam)), _p(_f64(src)), _p(_f64(dst)), _p(_f64(nor)), _p(r), _p(jac))
+    return r[:nr].copy(), jac[:nr * G].reshape(nr, G).copy()
 
 
 def _p(a, t=C.c_double):

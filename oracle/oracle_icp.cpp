@@ -710,6 +710,24 @@ void orc_quat_from_matrix(const double* R9, double* q4) { quat_from_matrix(R9, q
 void orc_quat_to_matrix(const double* q4, double* R9) { quat_to_matrix(q4, R9); }
 void orc_quat_transform(const double* q4, const double* v, double* out) { quat_transform(q4, v, out); }
 void orc_quat_plus(const double* x4, const double* d3, double* out4) { eigen_quat_plus(x4, d3, out4); }
+void orc_quat_jacobian(const double* x4, double* jac12) { eigen_quat_jacobian(x4, jac12); }
+// One restated multiview functor (functor_p2p / functor_p2plane) differentiated with Jets as evaluate_t does: residuals r[NR] and
+// the ambient Jacobian jac[NR][2G] (G = 6 for aa, 7 for quat / se3).  Lets tests/test_oracle_functor_pin.py compare the
+// restatement with the reference's own functor text compiled into oracle/_ref/libref_functors.so (oracle/ref_functors.cpp).
+void orc_functor_eval(int param, int plane, const double* cam1, const double* cam2, const double* src, const double* dst,
+                      const double* nor, double* r, double* jac) {
+  auto run = [&](auto tag_g, auto tag_p) {
+    constexpr int GG = decltype(tag_g)::value; constexpr int PP = decltype(tag_p)::value;
+    Jet<2 * GG> c1[GG], c2[GG], rj[3];
+    for (int i = 0; i < GG; ++i) { c1[i] = Jet<2 * GG>(cam1[i], i); c2[i] = Jet<2 * GG>(cam2[i], GG + i); }
+    if (plane) functor_p2plane<PP>(c1, c2, src, dst, nor, rj); else functor_p2p<PP>(c1, c2, src, dst, rj);
+    const int nr = plane ? 1 : 3;
+    for (int q = 0; q < nr; ++q) { r[q] = rj[q].a; for (int k = 0; k < 2 * GG; ++k) jac[q * 2 * GG + k] = rj[q].v[k]; }
+  };
+  if (param == PARAM_AA) run(std::integral_constant<int, 6>(), std::integral_constant<int, PARAM_AA>());
+  else if (param == PARAM_QUAT) run(std::integral_constant<int, 7>(), std::integral_constant<int, PARAM_QUAT>());
+  else run(std::integral_constant<int, 7>(), std::integral_constant<int, PARAM_SE3>());
+}
 void orc_angle_axis_rotate(const double* aa, const double* p, double* out) { angle_axis_rotate_point(aa, p, out); }
 void orc_rotmat_to_angle_axis(const double* R9, double* aa) { rotation_matrix_to_angle_axis(R9, aa); }
 void orc_angle_axis_to_rotmat(const double* aa, double* R9) { angle_axis_to_rotation_matrix(aa, R9); }

@@ -13,6 +13,12 @@ dino_pair.npz    the reference's second sample set, samples/dinosaur/cloud_{1,2}
                  in mm); pins the fp32 screening bound at a different coordinate magnitude.
 lm_golden.npz    oracle LM outputs (final poses, iteration trace) on a small seeded synthetic scene for every
                  parameterisation x cost; pins the oracle against accidental change (NOT against Ceres: unpinned).
+bunny18.npz      the reference's DEFAULT multiview workload (main_multiview.cpp:33-36,63: --limit=40 --step=2 on Bunny_RealData): the 18
+                 scans cloudXYZ_{0,2,..,34}.xyz (224 673 points; xyz only -- the default run recomputes the normals; stored as int32
+                 units of 1e-8 m, which is lossless for the <= 8-decimal text: parsed double == int / 1e8 exactly) with poses_{0,2,..,34}.txt
+                 (ground truth, non-rigid: singular values 1, 0.9957, 0.9957) and the initial poses of main_multiview.cpp:78-84
+                 (frame 0 = GT, the others addNoise(GT, 0.02, 0.01), common.h:38-67; the reference's default-seeded mt19937 stream
+                 is not reproduced -- same noise model, numpy seed 0xB18).  Used by `bench.py --config real` and tests/test_gpu_real18.py.
 sophus_vectors.npz  the SE3 group elements / tangents of ext/sophus-ceres/test/core/test_se3.cpp:40-82 (values only).
 """
 import os
@@ -53,6 +59,27 @@ def dino_pair():
     print("dino_pair:", c[0].shape, c[1].shape, "inliers", len(first), "weight", w)
 
 
+def bunny18():
+    ids = list(range(0, 36, 2))
+    xyz, off, gt, init = [], [0], [], []
+    rng = np.random.default_rng(0xB18)
+    for k, i in enumerate(ids):
+        c = np.loadtxt(f"{REF}/cloudXYZ_{i}.xyz")[:, :3]
+        um = np.rint(c * 1e8).astype(np.int64)
+        assert np.abs(um).max() < 2 ** 31 and np.array_equal(um.astype(np.float64) / 1e8, c), "int32 x 1e-8 m must be lossless"
+        xyz.append(um.astype(np.int32)); off.append(off[-1] + len(c))
+        P = np.loadtxt(f"{REF}/poses_{i}.txt")
+        gt.append(P)
+        Q = P.copy()
+        if k > 0:   # addNoise (common.h:38-67): pose * SO3::exp(sigma w), translation += sigmat t
+            Q[:3, :3] = P[:3, :3] @ synth._so3_exp(rng.normal(0.0, 1.0, 3) * 0.02)
+            Q[:3, 3] = P[:3, 3] + rng.normal(0.0, 1.0, 3) * 0.01
+        init.append(Q)
+    np.savez_compressed(os.path.join(OUT, "bunny18.npz"), n_frames=len(ids), frame_ids=np.array(ids), offsets=np.array(off, np.int64),
+                        xyz_e8=np.concatenate(xyz), poses_gt=np.stack(gt), poses_init=np.stack(init))
+    print("bunny18:", off[-1], "points", os.path.getsize(os.path.join(OUT, "bunny18.npz")) / 1e6, "MB")
+
+
 def lm_golden():
     sc = synth.make_scene(4, 3000, config_id=7)
     edges = synth.ring_edges(4, 2)
@@ -90,4 +117,7 @@ def sophus_vectors():
 
 
 if __name__ == "__main__":
-    bunny_pair(); dino_pair(); lm_golden(); sophus_vectors()
+    only = sys.argv[1:]
+    for fn in (bunny_pair, dino_pair, lm_golden, sophus_vectors, bunny18):
+        if not only or fn.__name__ in only:
+            fn()
