@@ -40,12 +40,8 @@ typedef struct {
 } mvicp_config;
 enum { MVICP_FLAG_NO_SEED = 1,     /* do not seed the NN search with the previous round's match */
        MVICP_FLAG_NCCL_ONLY = 2,   /* sharded LM: exchange pair matrices with ncclAllReduce instead of peer-memory stores */
-       MVICP_FLAG_WARP_SEARCH = 4, /* experimental: warp-phased schedule of the NN search (same results; measured slower, see profiles/README.md) */
-       MVICP_FLAG_OBB_FAR = 16,    /* experimental: rounds without seeds, or right after an LM solve of >= 4 iterations, search a second
-                                      tree of hybrid oriented boxes (same results; csrc/far.cuh; the boxes were measured on a GPU when
-                                      they replaced the AABBs everywhere, the switching was not) */
-       MVICP_FLAG_GRAPH_WALK = 8   /* experimental: seeded rounds answer most queries by a certified walk on the dst cloud's neighbour
-                                      graph, tree search as fallback (same results; csrc/walk.cuh; not yet measured on a GPU) */ };
+       MVICP_FLAG_NO_OBB = 16      /* do not build the second node array of hybrid oriented boxes that the far rounds (no seeds yet /
+                                      first seeded round) search (csrc/far.cuh); same results, for A/B measurements */ };
 
 /* Ceres options that the reference sets (icp-ceres.cpp:66-89) or leaves at Ceres defaults. */
 typedef struct {

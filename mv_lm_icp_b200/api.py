@@ -16,9 +16,7 @@ TERMINATION = ["FUNCTION_TOLERANCE", "GRADIENT_TOLERANCE", "PARAMETER_TOLERANCE"
                "INVALID_STEPS", "EVAL_FAILURE"]
 FLAG_NO_SEED = 1
 FLAG_NCCL_ONLY = 2
-FLAG_WARP_SEARCH = 4
-FLAG_GRAPH_WALK = 8
-FLAG_OBB_FAR = 16
+FLAG_NO_OBB = 16
 
 
 def _p(a, t=C.c_double):

@@ -94,8 +94,8 @@ __device__ __forceinline__ void nn_search_obb(const FrameDev& fd, const ObbNode*
 template <bool F32>
 __global__ void __launch_bounds__(KNN_TILE)
 knn_far_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
-               const Tile* __restrict__ tiles, int32_t* __restrict__ corr, double* __restrict__ d2out,
-               const int32_t* __restrict__ seed, double thresh, const ObbDev* __restrict__ obbs) {
+               const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
+               const int32_t* seed, double thresh, const ObbDev* __restrict__ obbs) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ EdgeXf sx;

@@ -59,10 +59,21 @@ struct NNQuery {
   float bound32;
 };
 
+// r >= sqrt(b): the hardware's approximate square root (2 ulp, one MUFU) scaled up by 1 + 2^-20 instead of the correctly rounded
+// software sequence -- the bound only has to be an upper bound, and it is re-evaluated at every improvement of the best
+__device__ __forceinline__ float sqrt_upper(float b) {
+#ifdef __CUDA_ARCH__
+  float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return __fmul_ru(r, 1.00000095367431640625f);
+#else
+  return __fsqrt_ru(b);
+#endif
+}
+
 __device__ __forceinline__ void nn_tighten(NNQuery& s) {
   // (sqrt(best) + ea)^2 (1 + 1e-6), evaluated upward in fp32: b >= best, r >= sqrt(b)
   const float b = __double2float_ru(s.best);
-  const float r = __fsqrt_ru(b);
+  const float r = sqrt_upper(b);
   s.bound32 = __fmul_ru(__fmaf_ru(s.eaf, __fmaf_ru(2.0f, r, s.eaf), b), 1.000001f);
 }
 
@@ -176,104 +187,6 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_le
   }
 }
 
-// ---- warp-phased search (experimental, MVICP_FLAG_WARP_SEARCH) ---------------------------------------------------
-// Same search, same result, scheduled for a 32-wide warp.  In nn_search every lane alternates between "expand an internal
-// node" and "scan leaf points" on its own, so at most iterations the warp executes BOTH code paths (tools/sim_warp.py:
-// 24 of 32 lanes busy by trip count, 13 of 32 once the step type is accounted for).  Here the warp agrees on the phase:
-//   A  every lane that still has internal nodes on its stack expands one (children that are leaves go to a small per-lane
-//      leaf list instead of being scanned) -- until no lane has a node left or some lane's list is full;
-//   B  every lane scans the leaves it listed (a leaf = one 128-byte line of 8 float4, fully unrolled), nearest first,
-//      skipping those its bound has overtaken;
-// repeated until all stacks are empty.  The bound only tightens in B, which costs ~20 % more box tests for far queries
-// (tools/sim_phase.py) and buys type-uniform execution.  All 32 lanes must call this (valid = false: nothing to do).
-// Measured on B200 (profiles/README.md): round 0 3 % faster, steady rounds 23 % slower (64 registers, vote + list
-// overhead) than the per-lane schedule, which therefore stays the default.
-constexpr int NN_LEAFCAP = 16;
-template <bool F32>
-__device__ __forceinline__ void nn_scan_leaf(const FrameDev& fd, int leaf, NNQuery& s) {
-  const int64_t pos = (int64_t)leaf * LEAF;
-  if (pos >= fd.n) return;   // padding leaf of the implicit tree (reachable only while the bound is still infinite)
-  float4 r[LEAF];
-#pragma unroll
-  for (int j = 0; j < LEAF; ++j) r[j] = __ldg(fd.pts_sf + pos + j);
-#pragma unroll
-  for (int j = 0; j < LEAF; ++j)
-    if (pt_d32(r[j], s) <= s.bound32) nn_exact<F32>(fd, pos + j, r[j], s);
-}
-
-template <bool F32>
-__device__ __forceinline__ void nn_search_warp(const FrameDev& fd, NNQuery& s, int start_leaf, bool valid) {
-  constexpr unsigned FULL = 0xffffffffu;
-  const int L = fd.n_leaf_pad;
-  int stk_n[NN_STACK]; float stk_lb[NN_STACK]; int sp = 0;
-  int lf_n[NN_LEAFCAP]; float lf_lb[NN_LEAFCAP]; int nlf = 0;
-  if (valid) {
-    int leaf_node = -1;
-    if (start_leaf >= 0) {
-      leaf_node = L + start_leaf;
-      nn_scan_leaf<F32>(fd, start_leaf, s);
-      const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
-      const float4 u = __ldg(b), v = __ldg(b + 1);
-      const float ex = u.w - u.x, ey = v.x - u.y, ez = v.y - u.z;
-      if (s.bound32 > 16.0f * fmaf(ez, ez, fmaf(ey, ey, ex * ex))) start_leaf = -1;   // stale guess: see nn_search
-    }
-    if (start_leaf < 0) {
-      int node = 1;
-      while (node < L) {
-        const int c0 = 2 * node;
-        const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
-        node = (l1 < l0) ? c0 + 1 : c0;
-      }
-      if (node != leaf_node) nn_scan_leaf<F32>(fd, node - L, s);
-      leaf_node = node;
-    }
-    for (int l = fd.depth - 1; l >= 0; --l) {
-      const int sib = (leaf_node >> l) ^ 1;
-      const float face = __ldg(fd.faces + sib);
-      const int axis = __float_as_int(face) & 3;
-      const float qa = axis == 0 ? s.fx : (axis == 1 ? s.fy : s.fz);
-      const float dpl = (sib & 1) ? face - qa : qa - face;
-      if (dpl > 0.f && dpl * dpl > s.bound32) continue;
-      const float lb = box_lb32(fd.boxes, sib, s);
-      if (lb <= s.bound32) {
-        if (sib >= L) { lf_n[nlf] = sib; lf_lb[nlf] = lb; ++nlf; }
-        else { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
-      }
-    }
-  }
-  while (true) {
-    // phase A: expand internal nodes
-    while (true) {
-      if (__any_sync(FULL, nlf > NN_LEAFCAP - 2)) break;
-      int node = -1;
-      while (sp > 0) { --sp; if (stk_lb[sp] <= s.bound32) { node = stk_n[sp]; break; } }
-      if (!__any_sync(FULL, node >= 0)) break;
-      if (node >= 0) {
-        const int c0 = 2 * node;
-        const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
-        const bool first0 = l0 <= l1;
-        const int cn = first0 ? c0 : c0 + 1, cf = first0 ? c0 + 1 : c0;
-        const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
-        if (c0 >= L) {   // children are leaves: far one first, so that the near one is scanned first
-          if (lf <= s.bound32) { lf_n[nlf] = cf; lf_lb[nlf] = lf; ++nlf; }
-          if (ln <= s.bound32) { lf_n[nlf] = cn; lf_lb[nlf] = ln; ++nlf; }
-        } else {
-          if (lf <= s.bound32) { stk_n[sp] = cf; stk_lb[sp] = lf; ++sp; }
-          if (ln <= s.bound32) { stk_n[sp] = cn; stk_lb[sp] = ln; ++sp; }
-        }
-      }
-    }
-    // phase B: scan the listed leaves
-    while (true) {
-      int leaf = -1;
-      while (nlf > 0) { --nlf; if (lf_lb[nlf] <= s.bound32) { leaf = lf_n[nlf] - L; break; } }
-      if (!__any_sync(FULL, leaf >= 0)) break;
-      if (leaf >= 0) nn_scan_leaf<F32>(fd, leaf, s);
-    }
-    if (!__any_sync(FULL, sp > 0)) break;
-  }
-}
-
 __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, double qz, float absmax) {
   s.qx = qx; s.qy = qy; s.qz = qz;
   s.fx = (float)qx; s.fy = (float)qy; s.fz = (float)qz;
@@ -285,11 +198,11 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
 
 // One thread per (edge, src point) query; src points are walked in the src frame's tree order so that the
 // lanes of a warp descend the dst tree together.
-template <bool F32, bool WARP>
+template <bool F32>
 __global__ void __launch_bounds__(KNN_TILE)
 knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
-           const Tile* __restrict__ tiles, int32_t* __restrict__ corr, double* __restrict__ d2out,
-           const int32_t* __restrict__ seed, double thresh) {
+           const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
+           const int32_t* seed, double thresh) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ EdgeXf sx;
@@ -302,10 +215,9 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
   const FrameDev fs = frames[e.src];
   const FrameDev fd = frames[e.dst];
   const int ks = t.start + threadIdx.x;
-  const bool valid = ks < e.n_src;
-  if (!WARP && !valid) return;          // the warp-phased search needs all 32 lanes at its votes
-  double px = 0, py = 0, pz = 0; int orig = 0;
-  if (valid) Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
+  if (ks >= e.n_src) return;
+  double px, py, pz; int orig;
+  Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
   // g = R_s p + t_s
   const double gx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[0], px), __dmul_rn(sx.Rs[1], py)), __dmul_rn(sx.Rs[2], pz)), sx.ts[0]);
   const double gy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sx.Rs[3], px), __dmul_rn(sx.Rs[4], py)), __dmul_rn(sx.Rs[5], pz)), sx.ts[1]);
@@ -317,19 +229,16 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
 
   NNQuery nq; nn_query_init(nq, qx, qy, qz, fd.absmax);
   int start_leaf = -1;
-  if (seed && valid) {   // previous round's match: a valid first guess, the search stays exact
+  if (seed) {   // previous round's match: a valid first guess, the search stays exact
     const int sd = seed[e.off + orig];
     const int si = sd >= 0 ? sd : ~sd;
     if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
   }
-  if (WARP) nn_search_warp<F32>(fd, nq, start_leaf, valid);
-  else nn_search<F32, NNQuery>(fd, nq, start_leaf);
-  if (valid) {
-    const double best = nq.best; const int bi = nq.bi;
-    const bool inlier = __dsqrt_rn(best) < thresh;
-    corr[e.off + orig] = inlier ? bi : ~bi;
-    d2out[e.off + orig] = best;
-  }
+  nn_search<F32, NNQuery>(fd, nq, start_leaf);
+  const double best = nq.best; const int bi = nq.bi;
+  const bool inlier = __dsqrt_rn(best) < thresh;
+  corr[e.off + orig] = inlier ? bi : ~bi;
+  d2out[e.off + orig] = best;
 }
 
 template <bool F32>

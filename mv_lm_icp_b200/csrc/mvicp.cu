@@ -27,7 +27,6 @@
 #include "se3_math.cuh"
 #include "select.cuh"
 #include "types.cuh"
-#include "walk.cuh"
 
 using namespace mv;
 
@@ -78,11 +77,9 @@ struct mvicp_ctx {
   std::vector<int64_t> n_pts;
   std::vector<FrameDev> h_frames;
   std::vector<void*> frame_allocs;
-  DevBuf d_walk;               // WalkDev per frame (MVICP_FLAG_GRAPH_WALK only)
-  bool walk_ready = false;
-  DevBuf d_guess, d_gcand;     // median brackets per edge + their candidate keys (walk.cuh)
-  bool guess_armed = false;
-  DevBuf d_obb;                // ObbDev per frame (MVICP_FLAG_OBB_FAR only)
+  DevBuf d_obb;                // ObbDev per frame (unless MVICP_FLAG_NO_OBB)
+  int seeded_rounds = 0;       // consecutive mvicp_correspond calls that started from the previous call's matches
+  DevBuf d_single;             // result slot of mvicp_closest_point
   bool obb_ready = false;
   int last_lm_iters = 1 << 20; // LM iterations of the previous mvicp_optimize: large = the clouds are still far apart
   DevBuf d_frames, d_poses;
@@ -141,6 +138,8 @@ static void assign_edge_owners(mvicp_ctx* c) {
 // =================================================================================================
 #include "tree_build.h"
 
+extern "C" { static int refresh_after_fixed_change(mvicp_ctx* c); }
+
 static bool all_fp32(const double* v, int64_t n) {
   for (int64_t i = 0; i < n; ++i) if ((double)(float)v[i] != v[i]) return false;
   return true;
@@ -196,13 +195,19 @@ int mvicp_create(const mvicp_config* cfg, mvicp_ctx** out) {
   c->device = cfg ? cfg->device : 0;
   c->flags = cfg ? cfg->flags : 0;
   if (c->device < 0 || c->device >= ndev) { const int d = c->device; delete c; return fail(MVICP_ERR_INVALID, "device %d out of range", d); }
-  CU(cudaSetDevice(c->device));
-  if (cfg && cfg->stream) c->stream = (cudaStream_t)cfg->stream;
-  else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
-  CU(cudaMallocHost(&c->h_state, sizeof(LmState)));
-  CU(cudaHostAlloc((void**)&c->h_flag, sizeof(int32_t) * 8, cudaHostAllocMapped));
-  CU(cudaHostGetDevicePointer((void**)&c->d_flag, (void*)c->h_flag, 0));
+  auto init = [&]() -> int {
+    CU(cudaSetDevice(c->device));
+    if (cfg && cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+    else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+    CU(cudaMallocHost(&c->h_state, sizeof(LmState)));
+    CU(cudaHostAlloc((void**)&c->h_flag, sizeof(int32_t) * 8, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&c->d_flag, (void*)c->h_flag, 0));
+    RET(c->d_single.reserve(16));
+    return MVICP_OK;
+  };
+  const int rc = init();
+  if (rc != MVICP_OK) { const std::string keep = g_err; mvicp_destroy(c); g_err = keep; return rc; }   // frees whatever was created
   *out = c;
   return MVICP_OK;
 }
@@ -210,7 +215,7 @@ int mvicp_create(const mvicp_config* cfg, mvicp_ctx** out) {
 void mvicp_destroy(mvicp_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (int p = 0; p < MAX_PEERS; ++p) if (c->peer_x[p] && c->peer_x[p] != c->xbuf) cudaIpcCloseMemHandle(c->peer_x[p]);
   if (c->xbuf) cudaFree(c->xbuf);
   if (c->comm) ncclCommDestroy(c->comm);
@@ -220,14 +225,14 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_walk, &c->d_obb, &c->d_guess, &c->d_gcand};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_obb, &c->d_single};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->h_flag) cudaFreeHost((void*)c->h_flag);
 
-  if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -304,7 +309,7 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
   c->fixed.assign(M, 0); c->fixed[0] = 1;
   c->E = 0; c->h_edges.clear(); c->have_corr = false;
   c->obb_ready = false; c->last_lm_iters = 1 << 20;
-  if (c->flags & MVICP_FLAG_OBB_FAR) {      // experimental: hybrid oriented boxes for the far rounds (far.cuh)
+  if (!(c->flags & MVICP_FLAG_NO_OBB)) {    // hybrid oriented boxes: a second node array for the far rounds (far.cuh)
     std::vector<ObbDev> ho(M);
     std::vector<std::vector<ObbHost>> obbs(M);
     {
@@ -325,32 +330,6 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     CU(cudaMemcpy(c->d_obb.p, ho.data(), sizeof(ObbDev) * M, cudaMemcpyHostToDevice));
     c->obb_ready = true;
   }
-  c->walk_ready = false;
-  if (c->flags & MVICP_FLAG_GRAPH_WALK) {   // experimental: neighbour lists + certificate radii of every cloud (walk.cuh)
-    std::vector<WalkDev> hw(M);
-    for (int f = 0; f < M; ++f) {
-      const int n = (int)n_pts[f], k = WALK_K + 2;
-      double* d_nor = nullptr; int32_t *d_nn = nullptr, *d_nbr = nullptr; double* d_r2 = nullptr;
-      CU(cudaMalloc(&d_nor, sizeof(double) * 3 * (size_t)n)); CU(cudaMalloc(&d_nn, sizeof(int32_t) * (size_t)k * n));
-      CU(cudaMalloc(&d_nbr, sizeof(int32_t) * (size_t)WALK_K * n)); c->frame_allocs.push_back(d_nbr);
-      CU(cudaMalloc(&d_r2, sizeof(double) * (size_t)n)); c->frame_allocs.push_back(d_r2);
-      if (f32) {
-        normals_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, k, d_nor, d_nn);
-        walk_build_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, d_nn, d_nbr, d_r2);
-      } else {
-        normals_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, k, d_nor, d_nn);
-        walk_build_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frames.as<FrameDev>(), f, d_nn, d_nbr, d_r2);
-      }
-      c->stats.kernel_launches += 2;
-      CU(cudaStreamSynchronize(c->stream));
-      cudaFree(d_nor); cudaFree(d_nn);
-      hw[f] = WalkDev{d_nbr, d_r2};
-    }
-    RET(c->d_walk.reserve(sizeof(WalkDev) * M));
-    CU(cudaMemcpy(c->d_walk.p, hw.data(), sizeof(WalkDev) * M, cudaMemcpyHostToDevice));
-    CU(cudaGetLastError());
-    c->walk_ready = true;
-  }
   return MVICP_OK;
 }
 
@@ -362,7 +341,7 @@ int mvicp_set_poses(mvicp_ctx* c, const double* poses16, const uint8_t* fixed) {
   std::memcpy(c->h_poses.data(), poses16, sizeof(double) * 16 * c->M);
   CU(cudaMemcpyAsync(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * c->M, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (fixed) c->fixed.assign(fixed, fixed + c->M);
+  if (fixed && !std::equal(fixed, fixed + c->M, c->fixed.begin())) { c->fixed.assign(fixed, fixed + c->M); RET(refresh_after_fixed_change(c)); }
   // Non-rigid "isometries" (e.g. the reference's Bunny_RealData sample poses) give non-unit quaternions, on which the
   // reference's quaternion / SE3 functors keep running (no normalisation, so3.hpp:666-668): remember it, the LM step
   // then uses the general frame model.  Sticky until the next upload: a fixed frame keeps its non-unit quaternion.
@@ -385,8 +364,9 @@ int mvicp_get_poses(mvicp_ctx* c, double* poses16) {
   return MVICP_OK;
 }
 
-// (re)build tile lists and per-edge buffers; called by set_graph and comm_init
-static int rebuild_work(mvicp_ctx* c) {
+// edge ownership, slot offsets and the tile lists of the NN / LM streaming kernels: depends on the graph, the cloud sizes, the
+// fixed flags and the rank layout -- not on the correspondences, which keep their slots
+static int layout_work(mvicp_ctx* c) {
   const int E = c->E;
   if (!E) return MVICP_OK;
   int64_t off = 0, owned_slots = 0;
@@ -414,6 +394,24 @@ static int rebuild_work(mvicp_ctx* c) {
   etb[E] = (int32_t)et.size();
   c->n_knn_tiles = (int)kt.size(); c->n_eval_tiles = (int)et.size();
   RET(c->d_edges.reserve(sizeof(EdgeDev) * E));
+  RET(c->d_knn_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, kt.size())));
+  RET(c->d_eval_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, et.size())));
+  RET(c->d_edge_tile_begin.reserve(sizeof(int32_t) * (E + 1)));
+  RET(c->d_partial.reserve(sizeof(double) * NBLK * std::max<size_t>(1, et.size())));
+  CU(cudaMemcpy(c->d_edges.p, c->h_edges.data(), sizeof(EdgeDev) * E, cudaMemcpyHostToDevice));
+  if (!kt.empty()) CU(cudaMemcpy(c->d_knn_tiles.p, kt.data(), sizeof(Tile) * kt.size(), cudaMemcpyHostToDevice));
+  if (!et.empty()) CU(cudaMemcpy(c->d_eval_tiles.p, et.data(), sizeof(Tile) * et.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_edge_tile_begin.p, etb.data(), sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice));
+  ++c->graph_gen;
+  return MVICP_OK;
+}
+
+// (re)build tile lists and per-edge buffers, forgetting every correspondence; called by set_graph and comm_init
+static int rebuild_work(mvicp_ctx* c) {
+  const int E = c->E;
+  if (!E) return MVICP_OK;
+  RET(layout_work(c));
+  const int64_t off = c->total_slots;
   RET(c->d_xf.reserve(sizeof(EdgeXf) * E));
   RET(c->d_corr.reserve(sizeof(int32_t) * off));
   RET(c->d_d2.reserve(sizeof(double) * off));
@@ -424,16 +422,6 @@ static int rebuild_work(mvicp_ctx* c) {
   RET(c->d_median.reserve(sizeof(double) * E));
   RET(c->d_selcand.reserve(sizeof(unsigned long long) * SEL_CAP * (size_t)E));
   RET(c->d_selcand_n.reserve(sizeof(unsigned int) * E));
-  if (c->flags & MVICP_FLAG_GRAPH_WALK) { RET(c->d_guess.reserve(sizeof(SelGuess) * E)); RET(c->d_gcand.reserve(sizeof(unsigned long long) * GUESS_CAP * (size_t)E)); }
-  c->guess_armed = false;
-  RET(c->d_knn_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, kt.size())));
-  RET(c->d_eval_tiles.reserve(sizeof(Tile) * std::max<size_t>(1, et.size())));
-  RET(c->d_edge_tile_begin.reserve(sizeof(int32_t) * (E + 1)));
-  RET(c->d_partial.reserve(sizeof(double) * NBLK * std::max<size_t>(1, et.size())));
-  CU(cudaMemcpy(c->d_edges.p, c->h_edges.data(), sizeof(EdgeDev) * E, cudaMemcpyHostToDevice));
-  if (!kt.empty()) CU(cudaMemcpy(c->d_knn_tiles.p, kt.data(), sizeof(Tile) * kt.size(), cudaMemcpyHostToDevice));
-  if (!et.empty()) CU(cudaMemcpy(c->d_eval_tiles.p, et.data(), sizeof(Tile) * et.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->d_edge_tile_begin.p, etb.data(), sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice));
   CU(cudaMemset(c->d_hist.p, 0, sizeof(unsigned int) * SEL_BINS * (size_t)E));
   CU(cudaMemset(c->d_weight.p, 0, sizeof(float) * E));
   CU(cudaMemset(c->d_selcand_n.p, 0, sizeof(unsigned int) * E));
@@ -441,8 +429,18 @@ static int rebuild_work(mvicp_ctx* c) {
   CU(cudaMemset(c->d_corr.p, 0xff, sizeof(int32_t) * off));   // ~0 = "no inlier, candidate 0"
   c->h_weight.assign(E, 0.f); c->h_count.assign(E, 0ull);
   c->have_corr = false;
-  ++c->graph_gen;
   return MVICP_OK;
+}
+
+// The fixed flags changed after the graph was laid out (mvicp_set_poses, or mvicp_optimize fixing frame 0 as every
+// ceresOptimizer* does, icp-ceres.cpp:242-244): the reference keeps working with whatever correspondences exist and only skips
+// the edges of fixed src frames (`if(srcCloud.fixed) continue;` icp-ceres.cpp:255,353,426).  On one GPU ownership is exactly
+// "src is free", so the layout is refreshed and the correspondences stay; sharded, edges would change ranks: everything is
+// laid out again and the next mvicp_correspond refills it.
+static int refresh_after_fixed_change(mvicp_ctx* c) {
+  if (!c->E) return MVICP_OK;
+  CU(cudaStreamSynchronize(c->stream));
+  return c->world > 1 ? rebuild_work(c) : layout_work(c);
 }
 
 int mvicp_set_graph(mvicp_ctx* c, int32_t E, const int32_t* src, const int32_t* dst) {
@@ -488,56 +486,39 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
-  bool hist0_done = false;   // the walk kernel delivers the select's first histogram itself
-  // converged rounds (the previous LM solve took one iteration: poses unchanged up to conversion rounding): the walk kernel
-  // also brackets the median, and one small kernel per edge replaces the whole select (walk.cuh)
-  const bool use_guess = seed && c->walk_ready && c->guess_armed && c->last_lm_iters <= 1;
   if (c->n_knn_tiles) {
-    // experimental far-round kernel: no seeds yet, or the previous LM solve still needed several iterations (far.cuh)
-    const bool far = c->obb_ready && (!seed || c->last_lm_iters >= 4);
+    // Far rounds search the oriented-box node array (far.cuh): a round without seeds, and the first round that has them (its
+    // seeds were found before the first LM solve moved the clouds by centimetres).  Measured on config 3 (profiles/r2): round 0
+    // 11.1 -> 9.0 ms, round 1 6.6 -> 5.9 ms; from the second seeded round on the 32-byte AABB nodes win (4.57 vs 4.96 ms).
+    // Poses set from outside since the last solve count as a fresh start.
+    if (!seed || c->last_lm_iters == (1 << 20)) c->seeded_rounds = 0;
+    const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1);
+    if (seed) ++c->seeded_rounds;
     if (far) {
       knn_far_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
           c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
           c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh, c->d_obb.as<ObbDev>());
-    } else if (seed && c->walk_ready) {   // experimental: neighbour-graph walk with certificate, tree search as fallback (walk.cuh)
-      knn_walk_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
-          c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
-          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, c->d_walk.as<WalkDev>(),
-          use_guess ? nullptr : c->d_hist.as<unsigned int>(), use_guess ? c->d_guess.as<SelGuess>() : nullptr,
-          c->d_gcand.as<unsigned long long>());
-      hist0_done = true;
     } else {
-      auto kern = (c->flags & MVICP_FLAG_WARP_SEARCH) ? knn_kernel<F32, true> : knn_kernel<F32, false>;
-      kern<<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
+      knn_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
           c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
           c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh);
     }
   }
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);
-  if (use_guess && hist0_done) {
-    select_guess_finish_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
-                                                               c->d_sel.as<SelState>(), c->d_guess.as<SelGuess>(), c->d_gcand.as<unsigned long long>(),
-                                                               c->d_weight.as<float>(), c->d_median.as<double>(), c->d_count.as<unsigned long long>());
-    c->stats.kernel_launches += 1;
-    CU(cudaEventRecord(c->ev[2], c->stream));
-    CU(cudaGetLastError());
-    return MVICP_OK;
-  }
   // exact median -> weight
   select_init_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_sel.as<SelState>(), E);
   c->stats.kernel_launches += 1;
   const int shifts[2] = {53, 42};
   for (int p = 0; p < 2; ++p) {
-    const bool have = p == 0 && hist0_done;
-    if (c->n_eval_tiles && !have)
+    if (c->n_eval_tiles)
       select_hist_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(
           c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len, c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
           c->d_sel.as<SelState>(), shifts[p], 11, c->d_hist.as<unsigned int>());
     select_pick_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_hist.as<unsigned int>(), shifts[p], p == 0, 0,
                                                          c->d_weight.as<float>(), c->d_median.as<double>(),
                                                          c->d_count.as<unsigned long long>());
-    c->stats.kernel_launches += 1 + ((c->n_eval_tiles && !have) ? 1 : 0);
+    c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
   }
   if (c->n_eval_tiles)
     select_collect_kernel<<<c->n_eval_tiles, SEL_THREADS, 0, c->stream>>>(
@@ -547,11 +528,6 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
                                                          c->d_sel.as<SelState>(), c->d_selcand.as<unsigned long long>(),
                                                          c->d_selcand_n.as<unsigned int>(), c->d_weight.as<float>(), c->d_median.as<double>());
   c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
-  if (c->walk_ready) {   // bracket the exact median for a later converged round
-    select_guess_arm_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_sel.as<SelState>(), c->d_guess.as<SelGuess>(), E);
-    c->stats.kernel_launches += 1;
-    c->guess_armed = true;
-  }
   CU(cudaEventRecord(c->ev[2], c->stream));
   CU(cudaGetLastError());
   return MVICP_OK;
@@ -635,8 +611,7 @@ int mvicp_set_edge(mvicp_ctx* c, int32_t e, const int32_t* first, const int32_t*
 int mvicp_closest_point(mvicp_ctx* c, int32_t frame, const double q[3], int64_t* idx, double* d2) {
   if (!c || frame < 0 || frame >= c->M || !q) return fail(MVICP_ERR_INVALID, "mvicp_closest_point: bad arguments");
   CU(cudaSetDevice(c->device));
-  long long* d_i; double* d_d;
-  CU(cudaMalloc(&d_i, 8)); CU(cudaMalloc(&d_d, 8));
+  long long* d_i = c->d_single.as<long long>(); double* d_d = c->d_single.as<double>() + 1;
   if (c->f32) knn_single_kernel<true><<<1, 1, 0, c->stream>>>(c->d_frames.as<FrameDev>(), frame, q[0], q[1], q[2], d_i, d_d);
   else knn_single_kernel<false><<<1, 1, 0, c->stream>>>(c->d_frames.as<FrameDev>(), frame, q[0], q[1], q[2], d_i, d_d);
   c->stats.kernel_launches += 1;
@@ -644,7 +619,6 @@ int mvicp_closest_point(mvicp_ctx* c, int32_t frame, const double q[3], int64_t*
   CU(cudaMemcpyAsync(&hi, d_i, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(&hd, d_d, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  cudaFree(d_i); cudaFree(d_d);
   if (idx) *idx = hi;
   if (d2) *d2 = hd;
   return MVICP_OK;
@@ -716,7 +690,10 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   for (int e = 0; e < E; ++e) {
     if ((c->edge_owner[e] < 0) != (c->fixed[c->h_edges[e].src] != 0)) stale = true;
   }
-  if (stale) return fail(MVICP_ERR_STATE, "fixed flags changed after mvicp_set_graph: call mvicp_set_graph again");
+  if (stale) {
+    if (c->world > 1) return fail(MVICP_ERR_STATE, "sharded run: frame 0 was free when the edges were distributed; fix it (mvicp_set_poses) before mvicp_correspond");
+    RET(refresh_after_fixed_change(c));
+  }
   // the gather lists / envelope depend only on the graph and the fixed flags: build and upload them when those change
   std::vector<uint8_t> key(c->fixed); key.push_back((uint8_t)(c->graph_gen & 0xff)); key.push_back((uint8_t)((c->graph_gen >> 8) & 0xff));
   if (key != c->lm_key) {
@@ -884,6 +861,8 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   }
   CU(cudaEventRecord(c->ev[4], c->stream));
   CU(cudaMemcpyAsync(c->h_state, c->d_state.p, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+  // the host mirror follows the device: mvicp_pose_graph_knn and mvicp_set_poses' "same poses as last handed out" test read it
+  CU(cudaMemcpyAsync(c->h_poses.data(), c->d_poses.p, sizeof(double) * 16 * M, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   std::memcpy(&st, c->h_state, sizeof st);
   CU(cudaGetLastError());
@@ -984,21 +963,51 @@ int mvicp_pairwise_closed(const mvicp_config* cfg, int32_t cost, const double* s
     CUX(cudaMemcpyAsync(d_aux, sums, sizeof sums, cudaMemcpyHostToDevice, st));
     closed_reduce_kernel<1><<<grid, CLOSED_THREADS, 0, st>>>(d_src, d_dst, nullptr, (long long)n, d_aux, d_part);
     if (fetch(9, K9)) { cleanup(); return fail(MVICP_ERR_CUDA, "mvicp_pairwise_closed: reduction failed: %s", cudaGetErrorString(cudaGetLastError())); }
-    // R = U V^T of K (its orthogonal polar factor) = K V diag(1/sigma) V^T with K^T K = V diag(sigma^2) V^T; the reference's
+    // R = U V^T with K = U S V^T (icp-closedform.cpp:18-19, JacobiSVD).  V and S^2 come from the symmetric eigen-decomposition of
+    // K^T K; u_j = K v_j / s_j only for the two largest singular values, u_3 = +-(u_1 x u_2) with the sign that keeps s_3 >= 0:
+    // a rank-deficient K (coplanar / collinear centred clouds, n < 3) then still yields an orthonormal U as the reference's SVD
+    // does, and a thin cloud does not pay the squared condition number on its smallest singular value.  Then the reference's
     // `R.col(2) *= -1` when det R < 0 (icp-closedform.cpp:20-22); t = qbar - R pbar
     double S[3][3], w[3], V[3][3], R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { S[a][b] = 0; for (int k = 0; k < 3; ++k) S[a][b] += K9[3 * k + a] * K9[3 * k + b]; }
     host_eig_sym3(S, w, V);
-    for (int j = 0; j < 3; ++j) {
-      const double sg = std::sqrt(w[j] > 0 ? w[j] : 0.0);
-      for (int a = 0; a < 3; ++a) { double u = 0; for (int k = 0; k < 3; ++k) u += K9[3 * a + k] * V[k][j]; u /= sg; for (int b = 0; b < 3; ++b) R[a][b] += u * V[b][j]; }
+    int ord[3] = {0, 1, 2};
+    std::sort(ord, ord + 3, [&](int x, int y) { return w[x] > w[y]; });
+    double U[3][3], Vs[3][3];   // columns j = singular triplets, descending
+    for (int j = 0; j < 3; ++j) for (int a = 0; a < 3; ++a) Vs[a][j] = V[a][ord[j]];
+    auto Kv = [&](int j, double out[3]) { for (int a = 0; a < 3; ++a) { out[a] = 0; for (int k = 0; k < 3; ++k) out[a] += K9[3 * a + k] * Vs[k][j]; } };
+    auto nrm = [](const double v[3]) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    double u0[3], u1[3], u2[3];
+    Kv(0, u0); const double s0 = nrm(u0);
+    if (s0 > 0) { for (int a = 0; a < 3; ++a) u0[a] /= s0; } else { u0[0] = 1; u0[1] = u0[2] = 0; }
+    Kv(1, u1);
+    { const double d = u1[0] * u0[0] + u1[1] * u0[1] + u1[2] * u0[2]; for (int a = 0; a < 3; ++a) u1[a] -= d * u0[a]; }
+    double s1 = nrm(u1);
+    if (s1 > 1e-13 * s0 && s1 > 0) { for (int a = 0; a < 3; ++a) u1[a] /= s1; }
+    else {   // rank <= 1: any unit vector orthogonal to u0
+      const int m = std::fabs(u0[0]) <= std::fabs(u0[1]) ? (std::fabs(u0[0]) <= std::fabs(u0[2]) ? 0 : 2) : (std::fabs(u0[1]) <= std::fabs(u0[2]) ? 1 : 2);
+      double e[3] = {0, 0, 0}; e[m] = 1;
+      const double d = u0[m]; for (int a = 0; a < 3; ++a) u1[a] = e[a] - d * u0[a];
+      s1 = nrm(u1); for (int a = 0; a < 3; ++a) u1[a] /= s1;
     }
+    u2[0] = u0[1] * u1[2] - u0[2] * u1[1]; u2[1] = u0[2] * u1[0] - u0[0] * u1[2]; u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+    {   // sign of u_3: s_3 = u_3 . K v_3 >= 0; when s_3 vanishes (rank-deficient K) either sign is an SVD -- take the proper rotation
+      double k2[3]; Kv(2, k2);
+      const double s2 = k2[0] * u2[0] + k2[1] * u2[1] + k2[2] * u2[2];
+      const double detV = Vs[0][0] * (Vs[1][1] * Vs[2][2] - Vs[1][2] * Vs[2][1]) - Vs[0][1] * (Vs[1][0] * Vs[2][2] - Vs[1][2] * Vs[2][0]) +
+                          Vs[0][2] * (Vs[1][0] * Vs[2][1] - Vs[1][1] * Vs[2][0]);
+      const bool neg = std::fabs(s2) > 1e-13 * s0 ? s2 < 0 : detV < 0;
+      if (neg) for (int a = 0; a < 3; ++a) u2[a] = -u2[a];
+    }
+    for (int a = 0; a < 3; ++a) { U[a][0] = u0[a]; U[a][1] = u1[a]; U[a][2] = u2[a]; }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int j = 0; j < 3; ++j) R[a][b] += U[a][j] * Vs[b][j];
     const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) + R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
     if (det < 0) for (int a = 0; a < 3; ++a) R[a][2] = -R[a][2];
     for (int a = 0; a < 3; ++a) {
       for (int b = 0; b < 3; ++b) pose16_out[4 * b + a] = R[a][b];
       pose16_out[12 + a] = sums[3 + a] - (R[a][0] * sums[0] + R[a][1] * sums[1] + R[a][2] * sums[2]);
     }
+    for (int i = 0; i < 16; ++i) if (!std::isfinite(pose16_out[i])) { cleanup(); return fail(MVICP_ERR_INVALID, "mvicp_pairwise_closed: non-finite result (non-finite input?)"); }
   } else {
     double v[27];
     closed_reduce_kernel<2><<<grid, CLOSED_THREADS, 0, st>>>(d_src, d_dst, d_nor, (long long)n, nullptr, d_part);
@@ -1015,6 +1024,7 @@ int mvicp_pairwise_closed(const mvicp_config* cfg, int32_t cost, const double* s
     const double ca = std::cos(x[0]), sa = std::sin(x[0]), cb = std::cos(x[1]), sb = std::sin(x[1]), cg = std::cos(x[2]), sg = std::sin(x[2]);
     const double R[3][3] = {{cb * cg, -cb * sg, sb}, {sa * sb * cg + ca * sg, -sa * sb * sg + ca * cg, -sa * cb}, {-ca * sb * cg + sa * sg, ca * sb * sg + sa * cg, ca * cb}};
     for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) pose16_out[4 * b + a] = R[a][b]; pose16_out[12 + a] = x[3 + a]; }   // Rx Ry Rz, t (:48-52)
+    for (int i = 0; i < 16; ++i) if (!std::isfinite(pose16_out[i])) { cleanup(); return fail(MVICP_ERR_INVALID, "mvicp_pairwise_closed: singular point-to-plane system (degenerate surface)"); }
   }
 #undef CUX
   cleanup();
@@ -1108,6 +1118,7 @@ int mvicp_comm_init(mvicp_ctx* c, const void* id128, int32_t rank, int32_t world
     int32_t okflag = ok ? 1 : 0;
     if (cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (world + 1) + 64) != cudaSuccess) return fail(MVICP_ERR_CUDA, "comm_init: cudaMalloc");
     char* dh = (char*)d_h;
+    struct Guard { void* p; ~Guard() { cudaFree(p); } } guard{d_h};   // released on every return path below
     CU(cudaMemcpy(dh, &mine, sizeof mine, cudaMemcpyHostToDevice));
     NC(ncclAllGather(dh, dh + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t), ncclUint8, c->comm, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1124,7 +1135,6 @@ int mvicp_comm_init(mvicp_ctx* c, const void* id128, int32_t rank, int32_t world
     NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemcpy(&okflag, d_ok, sizeof okflag, cudaMemcpyDeviceToHost));
-    cudaFree(d_h);
     c->p2p_ok = okflag == 1;
     c->xseq = 0;
   }

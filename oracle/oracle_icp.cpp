@@ -654,12 +654,40 @@ void orc_closed_p2p(const double* src, const double* dst, int64_t n, double* pos
   double S[3][3], w[3], V[3][3];
   for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { S[a][b] = 0; for (int c = 0; c < 3; ++c) S[a][b] += K[c][a] * K[c][b]; }
   eig3(S, w, V);
-  double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  // U column by column, largest singular value first; a (numerically) vanishing singular value leaves its column of U
+  // free up to orthonormality, as in JacobiSVD's full U: complete the basis with a cross product (rank 2) or an arbitrary
+  // perpendicular (rank 1) instead of dividing by ~0.
+  int o[3] = {0, 1, 2};
+  for (int i = 0; i < 3; ++i) for (int j = i + 1; j < 3; ++j) if (w[o[j]] > w[o[i]]) std::swap(o[i], o[j]);
+  double Uc[3][3], Vc[3][3], sig[3];
   for (int j = 0; j < 3; ++j) {
-    const double sg = std::sqrt(std::max(w[j], 0.0));
-    double u[3]; for (int a = 0; a < 3; ++a) { u[a] = 0; for (int c = 0; c < 3; ++c) u[a] += K[a][c] * V[c][j]; u[a] /= sg; }   // column j of U
-    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[a][b] += u[a] * V[b][j];
+    sig[j] = std::sqrt(std::max(w[o[j]], 0.0));
+    for (int a = 0; a < 3; ++a) { Vc[j][a] = V[a][o[j]]; Uc[j][a] = 0; for (int c = 0; c < 3; ++c) Uc[j][a] += K[a][c] * V[c][o[j]]; }
   }
+  auto unit = [](double* v) { const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); if (n > 0) { v[0] /= n; v[1] /= n; v[2] /= n; } return n; };
+  if (unit(Uc[0]) == 0) { Uc[0][0] = 1; Uc[0][1] = Uc[0][2] = 0; }
+  {
+    const double d = Uc[1][0] * Uc[0][0] + Uc[1][1] * Uc[0][1] + Uc[1][2] * Uc[0][2];
+    for (int a = 0; a < 3; ++a) Uc[1][a] -= d * Uc[0][a];
+    const double n1 = std::sqrt(Uc[1][0] * Uc[1][0] + Uc[1][1] * Uc[1][1] + Uc[1][2] * Uc[1][2]);
+    if (n1 > 1e-13 * sig[0] && n1 > 0) unit(Uc[1]);
+    else {
+      int m = 0; for (int a = 1; a < 3; ++a) if (std::fabs(Uc[0][a]) < std::fabs(Uc[0][m])) m = a;
+      for (int a = 0; a < 3; ++a) Uc[1][a] = (a == m ? 1.0 : 0.0) - Uc[0][m] * Uc[0][a];
+      unit(Uc[1]);
+    }
+  }
+  {
+    const double c[3] = {Uc[0][1] * Uc[1][2] - Uc[0][2] * Uc[1][1], Uc[0][2] * Uc[1][0] - Uc[0][0] * Uc[1][2], Uc[0][0] * Uc[1][1] - Uc[0][1] * Uc[1][0]};
+    // sigma_3 = c . K v_3 must be >= 0; if it vanishes both signs are valid SVDs and the proper rotation is taken
+    const double s3 = Uc[2][0] * c[0] + Uc[2][1] * c[1] + Uc[2][2] * c[2];
+    const double dV = Vc[0][0] * (Vc[1][1] * Vc[2][2] - Vc[1][2] * Vc[2][1]) - Vc[0][1] * (Vc[1][0] * Vc[2][2] - Vc[1][2] * Vc[2][0]) +
+                      Vc[0][2] * (Vc[1][0] * Vc[2][1] - Vc[1][1] * Vc[2][0]);
+    const double sgn = (std::fabs(s3) > 1e-13 * sig[0] ? s3 < 0 : dV < 0) ? -1.0 : 1.0;
+    for (int a = 0; a < 3; ++a) Uc[2][a] = sgn * c[a];
+  }
+  double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < 3; ++j) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[a][b] += Uc[j][a] * Vc[j][b];
   const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
                      R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
   if (det < 0) for (int a = 0; a < 3; ++a) R[a][2] *= -1;      // icp-closedform.cpp:20-22

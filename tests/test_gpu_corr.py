@@ -1,13 +1,11 @@
 """GPU parity of the correspondence step (mvicp_correspond) against the CPU oracle, through the C ABI.
 Bar: nearest-neighbour indices and squared distances bit-exact, inlier lists identical, float weight bit-exact."""
-import os
-
 import numpy as np
 import pytest
 
 from helpers import oracle_correspond, scene
 from mv_lm_icp_b200 import Engine, synth
-from mv_lm_icp_b200.api import FLAG_GRAPH_WALK, FLAG_NO_SEED, FLAG_OBB_FAR, FLAG_WARP_SEARCH
+from mv_lm_icp_b200.api import FLAG_NO_OBB, FLAG_NO_SEED
 
 pytestmark = pytest.mark.gpu
 
@@ -47,19 +45,16 @@ def test_synthetic_bit_exact(oracle, n_views, n_points, cfg):
     eng.close()
 
 
-# MVICP_FLAG_GRAPH_WALK and MVICP_FLAG_OBB_FAR have not run on a GPU yet (written after the round's GPU budget was spent; its logic is covered on
-# the host model, tests/test_hostemu_engine.py): the GPU suite includes it only on request.
-EXPERIMENTAL = ((FLAG_GRAPH_WALK, FLAG_GRAPH_WALK | FLAG_WARP_SEARCH, FLAG_OBB_FAR, FLAG_OBB_FAR | FLAG_NO_SEED, FLAG_OBB_FAR | FLAG_GRAPH_WALK)
-                if os.environ.get("MVICP_TEST_EXPERIMENTAL") else ())
+SCHEDULES = (FLAG_NO_SEED, FLAG_NO_OBB, FLAG_NO_OBB | FLAG_NO_SEED)
 
 
-def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=EXPERIMENTAL):
-    """Seeded / unseeded, warp-phased / per-lane search (and, on request, the certified graph walk): schedules of the same
+def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=()):
+    """Seeded / unseeded, with / without the oriented node boxes that the far rounds search (far.cuh): schedules of the same
     exact search, bit-identical output.  Odd cloud sizes leave partially filled warps and padding leaves in play."""
     sc = scene(4, 5003, 21)
     edges = synth.ring_edges(4, 2)
     res = []
-    for flags in (0, FLAG_NO_SEED, FLAG_WARP_SEARCH, FLAG_WARP_SEARCH | FLAG_NO_SEED) + tuple(extra_flags):
+    for flags in (0,) + SCHEDULES + tuple(extra_flags):
         eng = Engine(flags=flags)
         eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges)
         for poses in (sc["poses_init"], sc["poses_gt"], sc["poses_init"], sc["poses_init"]):   # cold, stale seeds twice, exact seeds

@@ -206,3 +206,30 @@ def test_full_size_round_matches_oracle(oracle):
     assert abs(summ["final_cost"] - sref["final_cost"]) <= 1e-9 * sref["final_cost"]
     assert pose_rel_err(P, Pref) <= TIGHT_TOL
     eng.close()
+
+
+def test_frame0_is_fixed_inside_the_optimiser():
+    """Every ceresOptimizer* sets frames[0]->fixed itself (icp-ceres.cpp:242-244,342-344,417-419) and works whether or not the
+    caller had set it before computeClosestPoints: same poses either way, and the pose graph built after a
+    solve sees the optimised poses."""
+    import mv_lm_icp_b200 as mv
+    sc = scene(4, 3000, 7)
+    out = []
+    for pre_fixed in (True, False):
+        frames = [mv.Frame(p, n, P) for p, n, P in zip(sc["pts"], sc["nor"], sc["poses_init"])]
+        icp = ICP_Ceres(frames)
+        frames[0].fixed = pre_fixed
+        icp.computePoseNeighbours(2)
+        for _ in range(2):
+            icp.computeClosestPoints(0.05)
+            icp.ceresOptimizer_sophusSE3(True, True)
+        assert frames[0].fixed
+        out.append(np.stack([f.pose for f in frames]))
+        g = icp.engine.pose_graph_knn(2)     # from the CURRENT poses: the engine's host mirror follows the solve
+        d = np.linalg.norm(out[-1][:, None, :3, 3] - out[-1][None, :, :3, 3], axis=2).astype(np.float32)
+        for i in range(4):
+            want = sorted((d[i, j], j) for j in range(4) if j != i)[:2]
+            assert [b for a, b in g if a == i] == [j for _, j in want]
+        icp.engine.close()
+    assert np.max(np.abs(out[0][0] - sc["poses_init"][0])) < 1e-14   # frame 0 only goes through the parameter round trip (icp-ceres.cpp:472-474)
+    assert np.max(np.abs(out[0] - out[1])) < 1e-12

@@ -25,13 +25,29 @@ def test_point_to_point_matches_oracle(oracle, n):
     dst = src @ R.T + t + np.random.default_rng(n).normal(0, 1e-4, src.shape)
     if n <= 3:
         T = ICP_Ceres.closed_form(src, dst)      # rank-deficient K (<= 3 points): the null direction of U V^T is a convention of the
-        assert T.shape == (4, 4)                 # SVD in the reference too -- no parity claim, the call just must not fail
+        R3 = T[:3, :3]                           # SVD in the reference too -- but the result is a finite proper rotation, as JacobiSVD's
+        assert np.all(np.isfinite(T)) and np.max(np.abs(R3 @ R3.T - np.eye(3))) < 1e-12 and np.linalg.det(R3) > 0
         return
     T, To = ICP_Ceres.closed_form(src, dst), oracle.closed_form(src, dst)
     assert np.max(np.abs(T - To)) < TOL
     if n >= 300:
         T = ICP_Ceres.closed_form(src, src @ R.T + t)             # exact correspondences: the transform itself
         assert np.max(np.abs(T[:3, :3] - R)) < 1e-11 and np.max(np.abs(T[:3, 3] - t)) < 1e-11
+
+
+def test_rank_deficient_clouds(oracle):
+    """Coplanar / collinear centred clouds: the cross-covariance has a vanishing singular value; the engine must
+    return the finite rotation an SVD yields (for a rigidly moved coplanar cloud: the motion itself), equal to the oracle's."""
+    rng = np.random.default_rng(11)
+    R = _rot(np.array([0.3, -0.5, 0.8])); t = np.array([0.2, -0.1, 0.05])
+    plane = rng.normal(size=(3000, 3)) * np.array([1.0, 0.6, 0.0])
+    T = ICP_Ceres.closed_form(plane, plane @ R.T + t)
+    assert np.max(np.abs(T[:3, :3] - R)) < 1e-11 and np.max(np.abs(T[:3, 3] - t)) < 1e-11
+    assert np.max(np.abs(T - oracle.closed_form(plane, plane @ R.T + t))) < 1e-11
+    line = np.outer(rng.normal(size=2000), np.array([0.3, -0.2, 0.9]))
+    T = ICP_Ceres.closed_form(line, line @ R.T + t)
+    assert np.all(np.isfinite(T)) and np.max(np.abs(T[:3, :3] @ T[:3, :3].T - np.eye(3))) < 1e-12 and np.linalg.det(T[:3, :3]) > 0
+    assert np.max(np.abs(line @ T[:3, :3].T + T[:3, 3] - (line @ R.T + t))) < 1e-11
 
 
 def test_reflection_branch_follows_the_reference(oracle):

@@ -50,8 +50,7 @@ def test_exports_every_abi_symbol(emu):
 def test_correspondence_step(emu, oracle, golden_dir):
     import test_gpu_corr as T
     T.test_synthetic_bit_exact(oracle, 4, 5000, 21)
-    T.test_seed_and_schedule_do_not_change_results(oracle, extra_flags=(T.FLAG_GRAPH_WALK, T.FLAG_GRAPH_WALK | T.FLAG_WARP_SEARCH, T.FLAG_OBB_FAR,
-                                                                        T.FLAG_OBB_FAR | T.FLAG_NO_SEED, T.FLAG_OBB_FAR | T.FLAG_GRAPH_WALK))
+    T.test_seed_and_schedule_do_not_change_results(oracle)
     T.test_real_bunny_pair_fp64_storage(oracle, golden_dir)
     import test_gpu_zz_dinosaur as TD
     TD.test_real_dinosaur_pair_mm_units(golden_dir)
@@ -76,6 +75,7 @@ def test_lm_pipeline_pairwise_and_general_path(emu, oracle, golden_dir):
         T.test_real_bunny_nonrigid_poses(oracle, golden_dir, 2, 1)
         return
     T.test_pipeline_round_matches_oracle(oracle)
+    T.test_frame0_is_fixed_inside_the_optimiser()
     for name, param, cost in (("pointToPoint_CeresAngleAxis", 0, 0), ("pointToPoint_EigenQuaternion", 1, 0), ("pointToPoint_SophusSE3", 2, 0),
                               ("pointToPlane_CeresAngleAxis", 0, 1), ("pointToPlane_EigenQuaternion", 1, 1), ("pointToPlane_SophusSE3", 2, 1)):
         T.test_pairwise_known_answer(oracle, golden_dir, name, param, cost)
@@ -140,20 +140,18 @@ def test_headless_driver_on_the_emulated_engine(emu, tmp_path):
         assert len(m) == 4 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m[1:]) and (extra or float(m[0][0]) < 1e-12)
 
 
-@pytest.mark.parametrize("xflags", [8, 16, 24], ids=["graph-walk", "obb-far", "both"])
-def test_experimental_schedules_are_bit_identical(emu, oracle, golden_dir, xflags):
-    """MVICP_FLAG_GRAPH_WALK (csrc/walk.cuh): seeded rounds answer most queries by a certified walk on the dst cloud's
-    neighbour graph; MVICP_FLAG_OBB_FAR (csrc/far.cuh): far rounds search a second tree of hybrid oriented boxes.  Same
-    matches, same distances, same poses as the default search -- over ICP rounds that go
-    from far (certificates fail, tree fallback) to converged (certificates hold), on fp32 and fp64 storage, with exact
-    duplicates and with clouds too small to have neighbour lists."""
+@pytest.mark.parametrize("xflags", [16, 17], ids=["no-obb", "no-obb-no-seed"])
+def test_schedules_are_bit_identical(emu, oracle, golden_dir, xflags):
+    """Default: far rounds (no seeds yet / first seeded round) test the internal nodes against hybrid oriented boxes (csrc/far.cuh).
+    MVICP_FLAG_NO_OBB: axis-aligned boxes only.  Same matches, same distances, same poses -- over ICP rounds that go from far to
+    converged, on fp32 and fp64 storage, with exact duplicates (ties -> lowest index) and with tiny clouds."""
     from helpers import scene
     from mv_lm_icp_b200 import Engine, synth
-    FLAG_GRAPH_WALK = xflags
+    XF = xflags
     sc = scene(4, 3001, 27)
     edges = synth.ring_edges(4, 2)
     runs = []
-    for flags in (0, FLAG_GRAPH_WALK):
+    for flags in (0, XF):
         eng = Engine(flags=flags); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
         out = []
         for rnd in range(6 if emu.order == "ascending" else 3):
@@ -167,7 +165,7 @@ def test_experimental_schedules_are_bit_identical(emu, oracle, golden_dir, xflag
     # fp64 storage, non-rigid poses, real scan (quantised coordinates): three slightly different poses, seeded
     g = np.load(f"{golden_dir}/bunny_pair.npz")
     res = []
-    for flags in (0, FLAG_GRAPH_WALK):
+    for flags in (0, XF):
         eng = Engine(flags=flags); eng.set_frames([g["pts0"], g["pts1"]], [g["nor0"], g["nor1"]]); eng.set_graph([(1, 0)])
         out = []
         for k in range(3):
@@ -182,7 +180,7 @@ def test_experimental_schedules_are_bit_identical(emu, oracle, golden_dir, xflag
     a = (rng.normal(size=(400, 3)) * 0.01).astype(np.float32).astype(np.float64); a[100:140] = a[0:40]
     b = a[::3] + np.float32(1e-4); tiny = a[:7].copy()
     res = []
-    for flags in (0, FLAG_GRAPH_WALK):
+    for flags in (0, XF):
         eng = Engine(flags=flags); eng.set_frames([a, b.astype(np.float32).astype(np.float64), tiny], None); eng.set_graph([(1, 0), (1, 2), (2, 0)])
         eng.set_poses([np.eye(4)] * 3, [1, 0, 0])
         out = []
@@ -227,27 +225,3 @@ print('ASAN RUN DONE')
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=1200, env=env)
     assert r.returncode == 0 and "ASAN RUN DONE" in r.stdout and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
-
-
-def test_median_bracket_replaces_the_select_in_converged_rounds(emu, oracle):
-    """With MVICP_FLAG_GRAPH_WALK, a round that follows a one-iteration LM solve brackets the median inside the NN kernel and
-    finishes it with one small kernel per edge (walk.cuh): fewer launches, the same weights, counts and poses bit for bit."""
-    _first_pass_only(emu)
-    from helpers import scene
-    from mv_lm_icp_b200 import Engine, synth
-    sc = scene(4, 12000, 3)
-    edges = synth.ring_edges(4, 2)
-    runs = []
-    for flags in (0, 8):
-        eng = Engine(flags=flags); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_gt"])
-        out = []; l0 = eng.stats()["kernel_launches"]
-        for rnd in range(10):
-            s = eng.icp_round(0.005, 2, 1, True); l1 = eng.stats()["kernel_launches"]
-            out.append((s["num_iterations"], eng.get_poses(), [eng.get_edge(e, arrays=False) for e in range(len(edges)) if edges[e][0] != 0], l1 - l0)); l0 = l1
-        runs.append(out); eng.close()
-    bracketed = 0
-    for (it0, P0, w0, n0), (it1, P1, w1, n1) in zip(*runs):
-        assert it0 == it1 and np.array_equal(P0.view(np.uint64), P1.view(np.uint64))
-        assert all(a[-2] == b[-2] and np.float32(a[-1]).view(np.uint32) == np.float32(b[-1]).view(np.uint32) for a, b in zip(w0, w1))
-        bracketed += int(n1 < n0)
-    assert bracketed >= 2 and runs[0][-1][0] == 1        # the scene converges to one-iteration solves; those rounds skip the select

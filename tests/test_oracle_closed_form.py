@@ -55,3 +55,20 @@ def test_closed_form_p2plane_is_the_linearised_solution(oracle):
     assert np.max(np.abs(T[:3, :3] - Rx @ Ry @ Rz)) < 1e-10 and np.max(np.abs(T[:3, 3] - x[3:])) < 1e-10
     # small motion: the linearisation is accurate to second order
     assert np.max(np.abs(T[:3, :3] - R)) < 1e-4 and np.max(np.abs(T[:3, 3] - t)) < 1e-4
+
+
+def test_closed_form_p2p_rank_deficient_clouds(oracle):
+    """Coplanar and collinear centred clouds (rank-2 / rank-1 cross-covariance): JacobiSVD still returns orthonormal U, V, so the
+    reference yields a finite rotation (icp-closedform.cpp:18-22); the restatement must too -- and for a
+    coplanar cloud moved rigidly it is the motion itself."""
+    rng = np.random.default_rng(11)
+    R = _rot(np.array([0.3, -0.5, 0.8])); t = np.array([0.2, -0.1, 0.05])
+    plane = rng.normal(size=(300, 3)) * np.array([1.0, 0.6, 0.0])
+    T = oracle.closed_form(plane, plane @ R.T + t)
+    assert np.max(np.abs(T[:3, :3] - R)) < 1e-12 and np.max(np.abs(T[:3, 3] - t)) < 1e-12
+    line = np.outer(rng.normal(size=200), np.array([0.3, -0.2, 0.9]))
+    T = oracle.closed_form(line, line @ R.T + t)
+    assert np.all(np.isfinite(T)) and np.max(np.abs(T[:3, :3] @ T[:3, :3].T - np.eye(3))) < 1e-12 and np.linalg.det(T[:3, :3]) > 0
+    assert np.max(np.abs(line @ T[:3, :3].T + T[:3, 3] - (line @ R.T + t))) < 1e-12      # maps the line onto its image
+    T = oracle.closed_form(plane[:2], plane[:2] @ R.T + t)                                   # n < 3
+    assert np.all(np.isfinite(T))

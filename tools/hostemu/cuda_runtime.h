@@ -135,6 +135,39 @@ inline int __any_sync(unsigned, int p) {
   hostemu::yield(hostemu::AT_WARP);
   return r;
 }
+inline unsigned __ballot_sync(unsigned, int p) {
+  const int w = hostemu::cur / 32, l = hostemu::cur % 32;
+  hostemu::vote_slot[w][l] = p ? 1 : 0;
+  hostemu::yield(hostemu::AT_WARP);
+  unsigned r = 0; for (int i = 0; i < 32; ++i) if (32 * w + i < hostemu::n_threads && hostemu::fibers[32 * w + i].state != hostemu::DONE && hostemu::vote_slot[w][i]) r |= 1u << i;
+  hostemu::yield(hostemu::AT_WARP);
+  return r;
+}
+// sub-warp collectives (mask names the participants): modelled on the whole-warp barrier, so every lane of the warp that is
+// still alive must reach SOME warp-level barrier while the named lanes exchange -- true for the engine's uses, where the
+// lanes outside the mask wait at the __syncwarp that follows.
+static long long match_slot[64][32]; static int match_in[64][32];
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+  const int w = hostemu::cur / 32, l = hostemu::cur % 32;
+  long long raw = 0; std::memcpy(&raw, &v, sizeof(T)); match_slot[w][l] = raw; match_in[w][l] = 1;
+  hostemu::yield(hostemu::AT_WARP);
+  unsigned r = 0; for (int i = 0; i < 32; ++i) if ((mask >> i & 1u) && match_in[w][i] && match_slot[w][i] == raw) r |= 1u << i;
+  hostemu::yield(hostemu::AT_WARP);
+  match_in[w][l] = 0;
+  return r;
+}
+template <class T> inline T __shfl_sync(unsigned, T v, int src, int = 32) {
+  static_assert(sizeof(T) <= 8, "shuffle of > 8 bytes");
+  const int w = hostemu::cur / 32, l = hostemu::cur % 32;
+  long long raw = 0; std::memcpy(&raw, &v, sizeof(T)); hostemu::warp_slot[w][l] = raw;
+  hostemu::yield(hostemu::AT_WARP);
+  raw = hostemu::warp_slot[w][src & 31]; T r; std::memcpy(&r, &raw, sizeof(T));
+  hostemu::yield(hostemu::AT_WARP);
+  return r;
+}
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 template <class T> inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicExch(T* p, T v) { const T o = *p; *p = v; return o; }
 inline void __threadfence() {} inline void __threadfence_system() {} inline void __threadfence_block() {}

@@ -1,17 +1,17 @@
 """Small end-to-end exercise of every kernel family, meant to be run under compute-sanitizer on a GPU box:
   compute-sanitizer --tool memcheck|racecheck|initcheck|synccheck --error-exitcode 1 python tools/sanitize_run.py
 (fp32 and fp64 storage, all three parameterisations, robust and plain, general non-rigid path, pairwise, normals, k-NN,
-single closest point, every NN schedule incl. the experimental graph walk).  Prints DONE at the end; results are not checked here (tests/ do that)."""
+single closest point, every NN schedule).  Prints DONE at the end; results are not checked here (tests/ do that)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mv_lm_icp_b200 as mv
 from mv_lm_icp_b200 import synth
-from mv_lm_icp_b200.api import FLAG_GRAPH_WALK, FLAG_OBB_FAR, FLAG_WARP_SEARCH, ICP_Ceres
+from mv_lm_icp_b200.api import FLAG_NO_OBB, FLAG_NO_SEED, ICP_Ceres
 
 sc = synth.make_scene(4, 1501, config_id=1)
 edges = synth.ring_edges(4, 2)
-for flags in (0, FLAG_WARP_SEARCH, FLAG_GRAPH_WALK, FLAG_OBB_FAR | FLAG_GRAPH_WALK):
+for flags in (0, FLAG_NO_SEED, FLAG_NO_OBB):
     eng = mv.Engine(device=0, flags=flags)
     eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
     for param in (mv.PARAM_SE3, mv.PARAM_QUAT, mv.PARAM_AA):
