@@ -38,7 +38,9 @@ typedef struct {
   int32_t flags;        /* MVICP_FLAG_*                                                       */
   void*   stream;       /* cudaStream_t to run on (NULL: the context creates its own)         */
 } mvicp_config;
-enum { MVICP_FLAG_NO_SEED = 1,     /* do not seed the NN search with the previous round's match */
+enum { MVICP_FLAG_HOST_BUILD = 4,  /* build the per-frame search trees on the host (csrc/tree_build.h) instead of on the device
+                                      (csrc/tree_gpu.cuh); same matches, for A/B measurements */
+       MVICP_FLAG_NO_SEED = 1,     /* do not seed the NN search with the previous round's match */
        MVICP_FLAG_NCCL_ONLY = 2,   /* sharded LM: exchange pair matrices with ncclAllReduce instead of peer-memory stores */
        MVICP_FLAG_NO_OBB = 16      /* do not build the second node array of hybrid oriented boxes that the far rounds (no seeds yet /
                                       first seeded round) search (csrc/far.cuh); same results, for A/B measurements */ };

@@ -16,6 +16,7 @@ TERMINATION = ["FUNCTION_TOLERANCE", "GRADIENT_TOLERANCE", "PARAMETER_TOLERANCE"
                "INVALID_STEPS", "EVAL_FAILURE"]
 FLAG_NO_SEED = 1
 FLAG_NCCL_ONLY = 2
+FLAG_HOST_BUILD = 4
 FLAG_NO_OBB = 16
 
 

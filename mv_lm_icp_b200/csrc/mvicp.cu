@@ -5,6 +5,9 @@
 // them.  No CPU fallback exists: every compute entry point fails with MVICP_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 #include <nccl.h>
+#ifdef __linux__
+#include <sched.h>
+#endif
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -137,8 +140,123 @@ static void assign_edge_owners(mvicp_ctx* c) {
 // one-time per-frame search structure (replaces the lazily built nanoflann index, frame.cpp:188-193)
 // =================================================================================================
 #include "tree_build.h"
+#include "tree_gpu.cuh"
 
 extern "C" { static int refresh_after_fixed_change(mvicp_ctx* c); }
+
+// worker threads for the one-time host work: the CPUs this process may use (affinity mask, cgroup v2 quota), not the machine's
+static unsigned host_workers() {
+  unsigned n = std::max(1u, std::thread::hardware_concurrency());
+#ifdef __linux__
+  cpu_set_t set; CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof set, &set) == 0) { const int k = CPU_COUNT(&set); if (k > 0) n = std::min<unsigned>(n, (unsigned)k); }
+  if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char q[32]; long long period = 0;
+    if (std::fscanf(f, "%31s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0) {
+      const long long quota = std::atoll(q);
+      if (quota > 0) n = std::min<unsigned>(n, (unsigned)std::max<long long>(1, quota / period));
+    }
+    std::fclose(f);
+  }
+#endif
+  return std::max(1u, n);
+}
+
+// common tail of mvicp_set_frames: frame table and identity poses on the device, graph and solver state reset
+static int finish_set_frames(mvicp_ctx* c, int M) {
+  RET(c->d_frames.reserve(sizeof(FrameDev) * M));
+  CU(cudaMemcpy(c->d_frames.p, c->h_frames.data(), sizeof(FrameDev) * M, cudaMemcpyHostToDevice));
+  RET(c->d_poses.reserve(sizeof(double) * 16 * M));
+  c->h_poses.assign((size_t)16 * M, 0.0);
+  for (int f = 0; f < M; ++f) for (int i = 0; i < 4; ++i) c->h_poses[16 * f + 5 * i] = 1.0;
+  CU(cudaMemcpy(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * M, cudaMemcpyHostToDevice));
+  c->fixed.assign(M, 0); c->fixed[0] = 1;
+  c->E = 0; c->h_edges.clear(); c->have_corr = false;
+  c->last_lm_iters = 1 << 20;
+  return MVICP_OK;
+}
+
+#ifdef __CUDACC__
+// Device construction of every frame's search structure (tree_gpu.cuh): raw coordinates go up once, everything else -- the
+// fp32-representability scan that picks the storage mode, the KD ordering, records, boxes, faces, oriented boxes -- is built there.
+template <bool F32>
+static int build_frames_on_device(mvicp_ctx* c, int M, const std::vector<double*>& d_xyz, const std::vector<double*>& d_nor,
+                                  const int64_t* n_pts, const std::vector<float>& absmax) {
+  const size_t rec = F32 ? sizeof(float4) : sizeof(double4a);
+  const bool want_obb = !(c->flags & MVICP_FLAG_NO_OBB);
+  KdScratch S;
+  std::vector<ObbDev> ho(M);
+  cudaError_t err = cudaSuccess;
+  for (int f = 0; f < M && err == cudaSuccess; ++f) {
+    const int n = (int)n_pts[f];
+    const int64_t n_leaf = std::max<int64_t>(1, ((int64_t)n + LEAF - 1) / LEAF);
+    int L = 1; while (L < n_leaf) L <<= 1;
+    int depth = 0; while ((1 << depth) < L) ++depth;
+    const int n_pad = (int)(n_leaf * LEAF);
+    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr, *d_fc = nullptr, *d_ob = nullptr;
+    auto grab = [&](void** p, size_t bytes) { if (err == cudaSuccess) { err = cudaMalloc(p, bytes); if (err == cudaSuccess) c->frame_allocs.push_back(*p); } };
+    grab(&d_o, rec * (size_t)n); grab(&d_s, rec * (size_t)n_pad); grab(&d_b, sizeof(Box) * 2 * (size_t)L); grab(&d_fc, sizeof(float) * 2 * (size_t)L);
+    grab(&d_pos, sizeof(int32_t) * (size_t)n);
+    if (F32) d_sf = d_s; else grab(&d_sf, sizeof(float4) * (size_t)n_pad);
+    if (d_nor[f]) grab(&d_n, rec * (size_t)n);
+    if (want_obb) grab(&d_ob, sizeof(ObbNode) * 2 * (size_t)L);
+    if (err != cudaSuccess) break;
+    const KdGeom g{n, L, depth};
+    err = kd_build_device<F32>(c->stream, S, d_xyz[f], g, d_s, (float4*)d_sf, (int32_t*)d_pos, (Box*)d_b, (float*)d_fc, (ObbNode*)d_ob,
+                               &c->stats.kernel_launches);
+    kd_pack_orig_kernel<F32><<<(n + 255) / 256, 256, 0, c->stream>>>(d_xyz[f], n, d_o);
+    if (d_nor[f]) kd_pack_orig_kernel<F32><<<(n + 255) / 256, 256, 0, c->stream>>>(d_nor[f], n, d_n);
+    c->stats.kernel_launches += d_nor[f] ? 2 : 1;
+    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n, L, depth, absmax[f]};
+    ho[f] = ObbDev{(const ObbNode*)d_ob};
+  }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+  S.release();
+  if (err != cudaSuccess) return fail(MVICP_ERR_CUDA, "device tree build: %s", cudaGetErrorString(err));
+  if (want_obb) {
+    RET(c->d_obb.reserve(sizeof(ObbDev) * M));
+    CU(cudaMemcpy(c->d_obb.p, ho.data(), sizeof(ObbDev) * M, cudaMemcpyHostToDevice));
+    c->obb_ready = true;
+  }
+  return MVICP_OK;
+}
+
+static int set_frames_device(mvicp_ctx* c, int M, const double* const* pts, const double* const* nor, const int64_t* n_pts) {
+  std::vector<double*> d_xyz(M, nullptr), d_nor(M, nullptr);
+  int* d_flags = nullptr;
+  auto cleanup = [&]() { for (double* p : d_xyz) cudaFree(p); for (double* p : d_nor) cudaFree(p); cudaFree(d_flags); };
+  std::vector<int> h_flags(4 * (size_t)M);
+  for (int f = 0; f < M; ++f) { h_flags[4 * f] = 1; h_flags[4 * f + 1] = 0; h_flags[4 * f + 2] = 1; h_flags[4 * f + 3] = 0; }
+  cudaError_t err = cudaMalloc(&d_flags, sizeof(int) * 4 * (size_t)M);
+  if (err == cudaSuccess) err = cudaMemcpy(d_flags, h_flags.data(), sizeof(int) * 4 * (size_t)M, cudaMemcpyHostToDevice);
+  for (int f = 0; f < M && err == cudaSuccess; ++f) {
+    const size_t bytes = sizeof(double) * 3 * (size_t)n_pts[f];
+    err = cudaMalloc(&d_xyz[f], bytes);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_xyz[f], pts[f], bytes, cudaMemcpyHostToDevice, c->stream);
+    if (err == cudaSuccess) kd_scan_kernel<<<2 * 148, 256, 0, c->stream>>>(d_xyz[f], 3ll * n_pts[f], d_flags + 4 * f);
+    if (err == cudaSuccess && nor && nor[f]) {
+      err = cudaMalloc(&d_nor[f], bytes);
+      if (err == cudaSuccess) err = cudaMemcpyAsync(d_nor[f], nor[f], bytes, cudaMemcpyHostToDevice, c->stream);
+      if (err == cudaSuccess) kd_scan_kernel<<<2 * 148, 256, 0, c->stream>>>(d_nor[f], 3ll * n_pts[f], d_flags + 4 * f + 2);
+    }
+    c->stats.kernel_launches += (nor && nor[f]) ? 2 : 1;
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(h_flags.data(), d_flags, sizeof(int) * 4 * (size_t)M, cudaMemcpyDeviceToHost, c->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+  if (err != cudaSuccess) { cleanup(); return fail(MVICP_ERR_CUDA, "mvicp_set_frames (upload): %s", cudaGetErrorString(err)); }
+  bool f32 = true; std::vector<float> absmax(M);
+  for (int f = 0; f < M; ++f) {
+    f32 = f32 && h_flags[4 * f] != 0 && h_flags[4 * f + 2] != 0;
+    std::memcpy(&absmax[f], &h_flags[4 * f + 1], 4);
+    if (!std::isfinite(absmax[f])) { cleanup(); return fail(MVICP_ERR_INVALID, "frame %d has a non-finite coordinate", f); }
+  }
+  c->f32 = f32; c->nor_f32 = f32;
+  c->h_frames.assign(M, FrameDev{});
+  const int rc = f32 ? build_frames_on_device<true>(c, M, d_xyz, d_nor, n_pts, absmax) : build_frames_on_device<false>(c, M, d_xyz, d_nor, n_pts, absmax);
+  cleanup();
+  return rc;
+}
+#endif
 
 static bool all_fp32(const double* v, int64_t n) {
   for (int64_t i = 0; i < n; ++i) if ((double)(float)v[i] != v[i]) return false;
@@ -250,13 +368,18 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     if (n_pts[f] > (int64_t)INT32_MAX / 2) return fail(MVICP_ERR_INVALID, "frame %d too large", f);
     if (!pts[f]) return fail(MVICP_ERR_INVALID, "frame %d: null points", f);
     if (!nor || !nor[f]) c->have_normals = false;
-    f32 = f32 && all_fp32(pts[f], 3 * n_pts[f]) && (!nor || !nor[f] || all_fp32(nor[f], 3 * n_pts[f]));
   }
-  c->f32 = f32; c->nor_f32 = f32; c->nor_dbl.clear();
+  c->nor_dbl.clear();
+  c->obb_ready = false;
+#ifdef __CUDACC__
+  if (!(c->flags & MVICP_FLAG_HOST_BUILD)) { RET(set_frames_device(c, M, pts, nor, n_pts)); return finish_set_frames(c, M); }
+#endif
+  for (int f = 0; f < M; ++f) f32 = f32 && all_fp32(pts[f], 3 * n_pts[f]) && (!nor || !nor[f] || all_fp32(nor[f], 3 * n_pts[f]));
+  c->f32 = f32; c->nor_f32 = f32;
   const size_t rec = f32 ? sizeof(float4) : sizeof(double4a);
   std::vector<HostFrameBuild> builds(M);
   {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned hw = host_workers();
     std::vector<std::thread> pool;
     std::atomic<int> next{0};
     for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)M); ++t)
@@ -300,20 +423,12 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n,
                               builds[f].n_leaf_pad, builds[f].depth, builds[f].absmax};
   }
-  RET(c->d_frames.reserve(sizeof(FrameDev) * M));
-  CU(cudaMemcpy(c->d_frames.p, c->h_frames.data(), sizeof(FrameDev) * M, cudaMemcpyHostToDevice));
-  RET(c->d_poses.reserve(sizeof(double) * 16 * M));
-  c->h_poses.assign((size_t)16 * M, 0.0);
-  for (int f = 0; f < M; ++f) for (int i = 0; i < 4; ++i) c->h_poses[16 * f + 5 * i] = 1.0;
-  CU(cudaMemcpy(c->d_poses.p, c->h_poses.data(), sizeof(double) * 16 * M, cudaMemcpyHostToDevice));
-  c->fixed.assign(M, 0); c->fixed[0] = 1;
-  c->E = 0; c->h_edges.clear(); c->have_corr = false;
-  c->obb_ready = false; c->last_lm_iters = 1 << 20;
+  c->last_lm_iters = 1 << 20;
   if (!(c->flags & MVICP_FLAG_NO_OBB)) {    // hybrid oriented boxes: a second node array for the far rounds (far.cuh)
     std::vector<ObbDev> ho(M);
     std::vector<std::vector<ObbHost>> obbs(M);
     {
-      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      const unsigned hw = host_workers();
       std::vector<std::thread> pool; std::atomic<int> next{0};
       for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)M); ++t)
         pool.emplace_back([&]() { for (int f; (f = next.fetch_add(1)) < M;) build_obb(pts[f], n_pts[f], builds[f], obbs[f]); });
@@ -330,7 +445,7 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     CU(cudaMemcpy(c->d_obb.p, ho.data(), sizeof(ObbDev) * M, cudaMemcpyHostToDevice));
     c->obb_ready = true;
   }
-  return MVICP_OK;
+  return finish_set_frames(c, M);
 }
 
 int mvicp_set_poses(mvicp_ctx* c, const double* poses16, const uint8_t* fixed) {

@@ -5,7 +5,7 @@ import pytest
 
 from helpers import oracle_correspond, scene
 from mv_lm_icp_b200 import Engine, synth
-from mv_lm_icp_b200.api import FLAG_NO_OBB, FLAG_NO_SEED
+from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_OBB, FLAG_NO_SEED
 
 pytestmark = pytest.mark.gpu
 
@@ -45,12 +45,13 @@ def test_synthetic_bit_exact(oracle, n_views, n_points, cfg):
     eng.close()
 
 
-SCHEDULES = (FLAG_NO_SEED, FLAG_NO_OBB, FLAG_NO_OBB | FLAG_NO_SEED)
+SCHEDULES = (FLAG_NO_SEED, FLAG_NO_OBB, FLAG_NO_OBB | FLAG_NO_SEED, FLAG_HOST_BUILD, FLAG_HOST_BUILD | FLAG_NO_SEED, FLAG_HOST_BUILD | FLAG_NO_OBB)
 
 
 def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=()):
-    """Seeded / unseeded, with / without the oriented node boxes that the far rounds search (far.cuh): schedules of the same
-    exact search, bit-identical output.  Odd cloud sizes leave partially filled warps and padding leaves in play."""
+    """Seeded / unseeded, with / without the oriented node boxes that the far rounds search (far.cuh), search trees built on the
+    device (tree_gpu.cuh, default) or on the host (tree_build.h): the same exact search, bit-identical output.  Odd cloud sizes
+    leave partially filled warps and padding leaves in play."""
     sc = scene(4, 5003, 21)
     edges = synth.ring_edges(4, 2)
     res = []
@@ -64,6 +65,26 @@ def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=()):
     for other in res[1:]:
         for (i0, d0), (i1, d1) in zip(res[0], other):
             assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
+
+
+def test_device_built_tree_is_a_valid_left_balanced_kd_tree():
+    """The structure tree_gpu.cuh builds, read back through the search: every point of a cloud is its own nearest neighbour at
+    distance 0 (ragged sizes around the leaf / level boundaries, a cloud with many equal coordinates, fp64 storage)."""
+    rng = np.random.default_rng(17)
+    clouds = [rng.normal(size=(n, 3)).astype(np.float32).astype(np.float64) * 0.05 for n in (1, 8, 9, 17, 64, 65, 1000, 4097, 30011)]
+    grid = np.stack(np.meshgrid(np.arange(20), np.arange(20), np.arange(3)), -1).reshape(-1, 3).astype(np.float64) * 0.01   # ties along every axis
+    clouds.append(grid)
+    clouds.append(rng.normal(size=(5000, 3)) * 0.05)      # not fp32-representable: every frame takes the fp64 records
+    for fp64 in (False, True):
+        cs = clouds if fp64 else clouds[:-1]
+        M = len(cs)
+        eng = Engine(); eng.set_frames(cs + cs, None)      # frame M + i is a copy of frame i: edge (M + i -> i) must match index to index
+        eng.set_graph([(M + i, i) for i in range(M)]); eng.set_poses([np.eye(4)] * (2 * M))
+        eng.correspond(0.05)
+        for i in range(M):
+            idx, d2 = eng.get_nn(i)
+            assert np.all(d2 == 0.0) and np.array_equal(idx, np.arange(len(cs[i]))), (fp64, i)
+        eng.close()
 
 
 def test_real_bunny_pair_fp64_storage(oracle, golden_dir):
