@@ -94,53 +94,72 @@ __global__ void lm_init_kernel(LmWork w) {
 // ---- dense Cholesky solve --------------------------------------------------------------------------------------
 // L: (n+1) rows of stride ld; rows 0..n-1 hold the lower triangle of the SPD matrix, row n holds the right-hand side
 // (treating the rhs as an extra row performs the forward substitution for free).  n is a multiple of 6 (one 6x6 block
-// per free pose), and the factorisation is right-looking over those blocks -- 2 barriers per pose instead of 2 per
-// column, which is what the single-CTA solve is bound by:
-//   (a) every thread factors the 6x6 diagonal block redundantly in registers (no communication),
-//   (b) panel: one thread per row below it solves its 6 entries against that block,
-//   (c) trailing update: one warp per row, lanes over columns, 6 multiply-adds per entry.
+// per free pose), and the factorisation is right-looking over those blocks with a one-block LOOK-AHEAD -- the solve is bound
+// by its dependent chain, not by arithmetic:
+//   panel     one thread per row below block J solves its 6 entries against the factored diagonal block;
+//   update    one warp per remaining row applies block J to the trailing matrix, while WARP 0 first updates the 21 entries
+//             of the NEXT diagonal block and factors it at once (registers, every lane the same arithmetic, lane 0 stores):
+//             the 6 x (rsqrt + dependent multiply-adds) of the next block overlap the other warps' update.
+// Two barriers per pose, and the 6x6 factor is computed once per block instead of once per thread (ncu, round 2: the
+// redundant factor with its software sqrt and division was 60 % of lm_step_kernel's instructions).  Diagonal entries are
+// inverted with rsqrt (1 ulp) and L_kk = d * rsqrt(d).
 // Rows whose profile starts right of the block (rfirst) and rows beyond rlast are structurally zero in the block
 // (envelope of the block-sparse normal matrix; fill-in stays inside each row's profile) and are skipped: only entries
 // inside the row profiles [rfirst[r], r] are ever read or written, the rest of L may hold anything.
-// scratch: >= 2n ints (row profiles staged in shared memory); dinv: reciprocal diagonal of the factor.
-// The back substitution runs block-wise in one warp.  Solution returned in y[0..n).
+// scratch: >= 2n + 1 ints (row profiles staged in shared memory + the "positive definite so far" flag); dinv: reciprocal
+// diagonal of the factor.  The back substitution runs block-wise in one warp.  Solution returned in y[0..n).
+__device__ __forceinline__ void chol_factor_diag(double* L, int ld, int j0, double* dinv, volatile int* s_ok, int lane) {
+  double D[6][6], inv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int k = 0; k <= i; ++k) D[i][k] = L[(size_t)(j0 + i) * ld + j0 + k];
+  bool okb = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double d = D[k][k];
+#pragma unroll
+    for (int m = 0; m < k; ++m) d -= D[k][m] * D[k][m];
+    if (!(d > 0.0) || !isfinite(d)) okb = false;
+    inv[k] = rsqrt(d); D[k][k] = d * inv[k];
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      double v = D[i][k];
+#pragma unroll
+      for (int m = 0; m < k; ++m) v -= D[i][m] * D[k][m];
+      D[i][k] = v * inv[k];
+    }
+  }
+  __syncwarp();   // every lane has read the block before lane 0 overwrites it
+  if (lane == 0) {
+    if (!okb) *s_ok = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int k = 0; k <= i; ++k) L[(size_t)(j0 + i) * ld + j0 + k] = D[i][k];
+      dinv[j0 + i] = inv[i];
+    }
+  }
+}
+
 __device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* dinv, double* y, const int32_t* __restrict__ rlast,
                            const int32_t* __restrict__ rfirst) {
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   int32_t* s_rfirst = reinterpret_cast<int32_t*>(scratch);
   int32_t* s_rlast = s_rfirst + n;
+  volatile int* s_ok = reinterpret_cast<volatile int*>(s_rlast + n);
   for (int i = tid; i < n; i += T) { s_rfirst[i] = rfirst[i]; s_rlast[i] = rlast[i]; }
+  if (tid == 0) *s_ok = 1;
+  __syncthreads();
   const int NB = n / 6;
+  if (wid == 0) chol_factor_diag(L, ld, 0, dinv, s_ok, lane);
+  __syncthreads();
   for (int J = 0; J < NB; ++J) {
+    if (!*s_ok) return false;                     // uniform: written before the last barrier
     const int j0 = 6 * J;
-    __syncthreads();
-    // (a) 6x6 diagonal block, lower triangle D[i][k] (k <= i), factored in place; every thread gets the same values
-    double D[6][6], inv[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int k = 0; k <= i; ++k) D[i][k] = L[(size_t)(j0 + i) * ld + j0 + k];
-    bool okb = true;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      double d = D[k][k];
-#pragma unroll
-      for (int m = 0; m < k; ++m) d -= D[k][m] * D[k][m];
-      if (!(d > 0.0) || !isfinite(d)) okb = false;
-      const double sd = sqrt(d);
-      inv[k] = 1.0 / sd; D[k][k] = sd;
-#pragma unroll
-      for (int i = k + 1; i < 6; ++i) {
-        double v = D[i][k];
-#pragma unroll
-        for (int m = 0; m < k; ++m) v -= D[i][m] * D[k][m];
-        D[i][k] = v * inv[k];
-      }
-    }
-    if (!okb) return false;                       // uniform: every thread computed the same block
     const int rl = s_rlast[j0 + 5];
     const int nrows = rl - (j0 + 5) + 1;          // rows j0+6..rl and the rhs row
-    // (b) panel: L[r][j0..j0+5] <- A[r][j0..j0+5] * L_JJ^-T
+    // panel: L[r][j0..j0+5] <- A[r][j0..j0+5] * L_JJ^-T
     for (int q = tid; q < nrows; q += T) {
       const int r = (q == nrows - 1) ? n : j0 + 6 + q;
       if (r < n && s_rfirst[r] > j0 + 5) continue;
@@ -150,41 +169,52 @@ __device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* di
       for (int k = 0; k < 6; ++k) {
         double a = row[k];
 #pragma unroll
-        for (int m = 0; m < k; ++m) a -= v[m] * D[k][m];
-        v[k] = a * inv[k];
+        for (int m = 0; m < k; ++m) a -= v[m] * L[(size_t)(j0 + k) * ld + j0 + m];
+        v[k] = a * dinv[j0 + k];
       }
 #pragma unroll
       for (int k = 0; k < 6; ++k) row[k] = v[k];
     }
     __syncthreads();
-    if (tid == T - 1) {                            // everybody has read the diagonal block by now: store its factor
+    // trailing update: A[r][c] -= sum_k L[r][j0+k] L[c][j0+k] for j0+5 < c <= min(r, rl)
+    const bool next = J + 1 < NB;
+    if (wid == 0 && next) {                       // look-ahead: the next diagonal block first, then its factor
+      const int b0 = j0 + 6;
+      if (lane < 21 && s_rfirst[b0] <= j0 + 5) {  // (the six rows of a pose share their profile start)
+        int i = 0, rem = lane; while (rem > i) { rem -= i + 1; ++i; }   // lane -> (i, k), k <= i
+        const int k = rem;
+        double* row = L + (size_t)(b0 + i) * ld; const double* lc = L + (size_t)(b0 + k) * ld + j0;
+        double a = row[b0 + k];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
+        for (int m = 0; m < 6; ++m) a -= row[j0 + m] * lc[m];
+        row[b0 + k] = a;
+      }
+      __syncwarp();
+      chol_factor_diag(L, ld, b0, dinv, s_ok, lane);
+    } else {
+      const int w0 = next ? 1 : 0, wn = next ? nw - 1 : nw;       // warps that share the remaining rows
+      const int qfirst = next ? 6 : 0;                              // rows of the next diagonal block belong to warp 0
+      for (int q = qfirst + (wid - w0); q < nrows; q += wn) {
+        const int r = (q == nrows - 1) ? n : j0 + 6 + q;
+        if (r < n && s_rfirst[r] > j0 + 5) continue;
+        double* row = L + (size_t)r * ld;
+        double lr[6];
 #pragma unroll
-        for (int k = 0; k <= i; ++k) L[(size_t)(j0 + i) * ld + j0 + k] = D[i][k];
-        dinv[j0 + i] = inv[i];
+        for (int k = 0; k < 6; ++k) lr[k] = row[j0 + k];
+        const int cend = min(r, rl);
+        for (int c = j0 + 6 + lane; c <= cend; c += 32) {
+          if (s_rfirst[c] > j0 + 5) continue;        // row c has nothing in this block: contributes exactly zero
+          const double* lc = L + (size_t)c * ld + j0;
+          double a = row[c];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) a -= lr[k] * lc[k];
+          row[c] = a;
+        }
       }
     }
-    // (c) trailing update: A[r][c] -= sum_k L[r][j0+k] L[c][j0+k] for j0+5 < c <= min(r, rl)
-    for (int q = wid; q < nrows; q += nw) {
-      const int r = (q == nrows - 1) ? n : j0 + 6 + q;
-      if (r < n && s_rfirst[r] > j0 + 5) continue;
-      double* row = L + (size_t)r * ld;
-      double lr[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) lr[k] = row[j0 + k];
-      const int cend = min(r, rl);
-      for (int c = j0 + 6 + lane; c <= cend; c += 32) {
-        if (s_rfirst[c] > j0 + 5) continue;        // row c has nothing in this block: contributes exactly zero
-        const double* lc = L + (size_t)c * ld + j0;
-        double a = row[c];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) a -= lr[k] * lc[k];
-        row[c] = a;
-      }
-    }
+    __syncthreads();
   }
-  __syncthreads();
+  if (!*s_ok) return false;
   for (int i = tid; i < n; i += T) y[i] = L[(size_t)n * ld + i];   // forward-substituted rhs
   __syncthreads();
   if (wid == 0) {
