@@ -12,6 +12,7 @@
 // (main_multiview.cpp:119-127): the per-frame member functions below therefore trigger the batched call when invoked
 // for the first non-fixed frame of a round and serve the other frames from the same result.
 #pragma once
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -30,6 +31,8 @@ struct Session {
   const std::vector<std::shared_ptr<FrameT>>* frames = nullptr;
   std::vector<int32_t> e_src, e_dst;
   bool corr_valid = false, graph_pushed = false;
+  struct Rec { int32_t first, second; double dist; };   // == struct Correspondance (frame.h:18-22)
+  std::vector<Rec> records;                              // staging of mvicp_get_all_edges
   ~Session() { mvicp_destroy(ctx); }
 
   void bind(const std::vector<std::shared_ptr<FrameT>>& fr) {
@@ -84,18 +87,22 @@ void computeClosestPoints(Session<FrameT>& s, std::vector<std::shared_ptr<FrameT
   s.push_poses();
   check(mvicp_correspond(s.ctx, cutoff));
   s.corr_valid = true;
+  // one call for every edge: counts / weights always, the 16-byte Correspondance records (bit-compatible with frame.h:18-22) on request
+  int32_t E = 0; for (auto& f : frames) E += (int32_t)f->neighbours.size();
+  std::vector<int64_t> off(E + 1); std::vector<float> w(E);
+  int64_t cap = 0; for (auto& f : frames) cap += (int64_t)f->neighbours.size() * (int64_t)f->pts.size();
+  if (materialize) s.records.resize((size_t)cap);
+  check(mvicp_get_all_edges(s.ctx, materialize ? (void*)s.records.data() : nullptr, cap, off.data(), w.data()));
   int32_t e = 0;
   for (auto& f : frames)
     for (auto& ne : f->neighbours) {
-      int64_t cnt = 0; float w = 0;
       if (!f->fixed) {
         if (materialize) {
-          std::vector<int32_t> a(f->pts.size()), b(f->pts.size()); std::vector<double> d(f->pts.size());
-          check(mvicp_get_edge(s.ctx, e, a.data(), b.data(), d.data(), &cnt, &w));
-          ne.correspondances.clear();
-          for (int64_t i = 0; i < cnt; ++i) ne.correspondances.push_back({a[i], b[i], d[i]});
-        } else check(mvicp_get_edge(s.ctx, e, nullptr, nullptr, nullptr, &cnt, &w));
-        ne.weight = w;
+          static_assert(sizeof(ne.correspondances[0]) == 16, "Correspondance {int, int, double}");
+          ne.correspondances.resize((size_t)(off[e + 1] - off[e]));
+          if (off[e + 1] > off[e]) std::memcpy((void*)ne.correspondances.data(), &s.records[(size_t)off[e]], 16 * (size_t)(off[e + 1] - off[e]));
+        }
+        ne.weight = w[e];
       }
       ++e;
     }

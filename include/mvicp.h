@@ -119,6 +119,12 @@ int mvicp_correspond(mvicp_ctx* ctx, float thresh);
  * Pass NULL arrays to query only count/weight. Arrays must hold n_pts[src] entries. */
 int mvicp_get_edge(mvicp_ctx* ctx, int32_t e, int32_t* first, int32_t* second, double* dist, int64_t* count,
                    float* weight);
+/* Every edge at once, for a caller that materialises OutgoingEdge::correspondances (the viewer draws them, Visualize.cpp:470-479):
+ * edge e's inliers are out_records[offsets[e] .. offsets[e+1]) as the reference's own 16-byte records
+ * struct Correspondance {int first; int second; double dist;} (include/frame.h:18-22), ascending src index (frame.cpp:156-160);
+ * weights[e] = OutgoingEdge::weight.  offsets has n_edges + 1 entries; out_records may be NULL (counts and weights only) and
+ * otherwise holds `capacity` records (sum of the src cloud sizes always suffices).  Built on the device, one copy back. */
+int mvicp_get_all_edges(mvicp_ctx* ctx, void* out_records, int64_t capacity, int64_t* offsets, float* weights /*nullable*/);
 /* Raw nearest neighbour of every src point of edge e (before the cutoff): index + squared distance, i.e. what
  * Frame::getClosestPoint returns per query (frame.cpp:187-206). */
 int mvicp_get_nn(mvicp_ctx* ctx, int32_t e, int32_t* nn_idx, double* nn_d2);

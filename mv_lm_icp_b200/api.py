@@ -117,17 +117,25 @@ class Engine:
         c = cnt.value
         return first[:c].copy(), second[:c].copy(), dist[:c].copy(), np.float32(w.value)
 
-    def pull_all_edges(self):
+    CORR_DTYPE = np.dtype([("first", np.int32), ("second", np.int32), ("dist", np.float64)])   # struct Correspondance (frame.h:18-22)
+
+    def pull_all_edges(self, records=True):
         """Every edge's (first, second, dist) list and weight into host arrays, as Frame::computeClosestPointsToNeighbours
-        leaves them in OutgoingEdge::correspondances (frame.cpp:158,176).  Returns the number of bytes that reached the host."""
-        nb = 0
-        self.host_edges = []
-        for e, (s, d) in enumerate(self.edges):
-            if s == 0:
-                self.host_edges.append(None); continue
-            f, sec, dist, w = self.get_edge(e)
-            self.host_edges.append((f, sec, dist, w)); nb += 16 * len(f) + 4
-        return nb
+        leaves them in OutgoingEdge::correspondances (frame.cpp:158,176): one structured array + offsets (mvicp_get_all_edges).
+        Returns the number of bytes that reached the host; self.host_edges[e] = (records view, weight)."""
+        E = len(self.edges)
+        off = np.zeros(E + 1, np.int64); w = np.zeros(E, np.float32)
+        cap = sum(self.n_pts[s] for s, _ in self.edges)
+        if records:
+            if getattr(self, "_rec_buf", None) is None or len(self._rec_buf) < cap:
+                self._rec_buf = np.empty(cap, self.CORR_DTYPE)
+            check(self._l.mvicp_get_all_edges(self._ctx, self._rec_buf.ctypes.data_as(C.c_void_p), C.c_int64(cap), _p(off, C.c_int64), _p(w, C.c_float)))
+            self.host_edges = [(self._rec_buf[off[e]:off[e + 1]], w[e]) for e in range(E)]
+        else:
+            check(self._l.mvicp_get_all_edges(self._ctx, None, C.c_int64(0), _p(off, C.c_int64), _p(w, C.c_float)))
+            self.host_edges = [(None, w[e]) for e in range(E)]
+        self.edge_offsets = off
+        return int(off[E]) * 16 * int(records) + 4 * E + 8 * (E + 1)
 
     def get_nn(self, e):
         n = self.n_pts[self.edges[e][0]]

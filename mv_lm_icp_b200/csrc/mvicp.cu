@@ -22,6 +22,7 @@
 
 #include "../../include/mvicp.h"
 #include "closed.cuh"
+#include "compact.cuh"
 #include "far.cuh"
 #include "knn.cuh"
 #include "lm_eval.cuh"
@@ -83,6 +84,7 @@ struct mvicp_ctx {
   DevBuf d_obb;                // ObbDev per frame (unless MVICP_FLAG_NO_OBB)
   int seeded_rounds = 0;       // consecutive mvicp_correspond calls that started from the previous call's matches
   DevBuf d_single;             // result slot of mvicp_closest_point
+  DevBuf d_tile_count, d_tile_off, d_edge_off, d_recs;   // mvicp_get_all_edges
   bool obb_ready = false;
   int last_lm_iters = 1 << 20; // LM iterations of the previous mvicp_optimize: large = the clouds are still far apart
   DevBuf d_frames, d_poses;
@@ -343,7 +345,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_obb, &c->d_single};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_obb, &c->d_single, &c->d_tile_count, &c->d_tile_off, &c->d_edge_off, &c->d_recs};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -688,6 +690,39 @@ int mvicp_get_edge(mvicp_ctx* c, int32_t e, int32_t* first, int32_t* second, dou
       }
     if (count) *count = n;
   }
+  return MVICP_OK;
+}
+
+int mvicp_get_all_edges(mvicp_ctx* c, void* out_records, int64_t capacity, int64_t* offsets, float* weights) {
+  if (!c || !c->E || !offsets) return fail(MVICP_ERR_INVALID, "mvicp_get_all_edges: bad arguments / no graph");
+  if (!c->have_corr) return fail(MVICP_ERR_STATE, "mvicp_get_all_edges: call mvicp_correspond first");
+  CU(cudaSetDevice(c->device));
+  const int E = c->E, nt = c->n_knn_tiles;
+  RET(c->d_tile_count.reserve(sizeof(unsigned int) * std::max(1, nt)));
+  RET(c->d_tile_off.reserve(sizeof(unsigned long long) * std::max(1, nt)));
+  RET(c->d_edge_off.reserve(sizeof(unsigned long long) * (E + 1)));
+  if (nt) compact_count_kernel<<<nt, KNN_TILE, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_knn_tiles.as<Tile>(), c->d_corr.as<int32_t>(), c->d_tile_count.as<unsigned int>());
+  compact_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_count.as<unsigned int>(), nt, c->d_knn_tiles.as<Tile>(), E,
+                                                 c->d_tile_off.as<unsigned long long>(), c->d_edge_off.as<unsigned long long>());
+  c->stats.kernel_launches += nt ? 2 : 1;
+  std::vector<unsigned long long> eo(E + 1);
+  CU(cudaMemcpyAsync(eo.data(), c->d_edge_off.p, sizeof(unsigned long long) * (E + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (weights) CU(cudaMemcpyAsync(weights, c->d_weight.p, sizeof(float) * E, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int e = 0; e <= E; ++e) offsets[e] = (int64_t)eo[e];
+  if (out_records) {
+    const int64_t total = (int64_t)eo[E];
+    if (total > capacity) return fail(MVICP_ERR_INVALID, "mvicp_get_all_edges: %lld records, capacity %lld", (long long)total, (long long)capacity);
+    if (total) {
+      RET(c->d_recs.reserve(sizeof(CorrRec) * (size_t)total));
+      compact_scatter_kernel<<<nt, KNN_TILE, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_knn_tiles.as<Tile>(), c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
+                                                             c->d_tile_off.as<unsigned long long>(), c->d_recs.as<CorrRec>());
+      c->stats.kernel_launches += 1;
+      CU(cudaMemcpyAsync(out_records, c->d_recs.p, sizeof(CorrRec) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+  }
+  CU(cudaGetLastError());
   return MVICP_OK;
 }
 

@@ -67,6 +67,30 @@ def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=()):
             assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
 
 
+def test_all_edges_in_one_call_equal_the_per_edge_lists(oracle):
+    """mvicp_get_all_edges (device-side compaction into the reference's 16-byte Correspondance records, one copy back) against
+    mvicp_get_edge per edge: same (first, second, dist) in the same order, same weights; edges of the fixed frame are empty."""
+    sc = scene(4, 5003, 21)
+    edges = synth.ring_edges(4, 2)
+    eng = Engine(); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges)
+    for poses, cut in ((sc["poses_init"], 0.05), (sc["poses_gt"], 0.0004)):     # nearly all inliers / a sparse subset
+        eng.set_poses(poses); eng.correspond(cut)
+        nb = eng.pull_all_edges()
+        assert nb == int(eng.edge_offsets[-1]) * 16 + 4 * len(edges) + 8 * (len(edges) + 1)
+        for e, (s, d) in enumerate(edges):
+            rec, w = eng.host_edges[e]
+            if s == 0:
+                assert len(rec) == 0
+                continue
+            f, sec, dist, ww = eng.get_edge(e)
+            assert np.array_equal(rec["first"], f) and np.array_equal(rec["second"], sec)
+            assert np.array_equal(rec["dist"].view(np.uint64), dist.view(np.uint64))
+            assert np.float32(w).view(np.uint32) == np.float32(ww).view(np.uint32)
+        eng.pull_all_edges(records=False)
+        assert all(r is None for r, _ in eng.host_edges)
+    eng.close()
+
+
 def test_device_built_tree_is_a_valid_left_balanced_kd_tree():
     """The structure tree_gpu.cuh builds, read back through the search: every point of a cloud is its own nearest neighbour at
     distance 0 (ragged sizes around the leaf / level boundaries, a cloud with many equal coordinates, fp64 storage)."""

@@ -57,6 +57,7 @@ def test_correspondence_step(emu, oracle, golden_dir):
     T.test_edge_cases(oracle)
     T.test_median_with_masses_of_near_equal_distances(oracle)
     T.test_closest_point_api(oracle)
+    T.test_all_edges_in_one_call_equal_the_per_edge_lists(oracle)
 
 
 @pytest.mark.parametrize("param", [0, 1, 2])

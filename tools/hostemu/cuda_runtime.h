@@ -117,6 +117,14 @@ template <class K, class... A> inline void hostemu_launch(K k, dim3 g, dim3 b, s
 
 inline void __syncthreads() { hostemu::yield(hostemu::AT_BLOCK); }
 inline void __syncwarp(unsigned = 0xffffffffu) { hostemu::yield(hostemu::AT_WARP); }
+static int block_vote[2048];
+inline int __syncthreads_count(int p) {
+  block_vote[hostemu::cur] = p ? 1 : 0;
+  hostemu::yield(hostemu::AT_BLOCK);
+  int r = 0; for (int i = 0; i < hostemu::n_threads; ++i) if (hostemu::fibers[i].state != hostemu::DONE) r += block_vote[i];
+  hostemu::yield(hostemu::AT_BLOCK);
+  return r;
+}
 template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta, int = 32) {
   static_assert(sizeof(T) <= 8, "shuffle of > 8 bytes");
   const int w = hostemu::cur / 32, l = hostemu::cur % 32;
