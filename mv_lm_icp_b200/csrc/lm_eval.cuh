@@ -99,8 +99,14 @@ lm_eval_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
     for (int u = 0; u < U; ++u)
       if (cidx[u] >= 0) {
         P[u] = rec_load<F32>(fs.pts_o, k0 + u * EVAL_THREADS);
-        Q[u] = rec_load<F32>(fd.pts_o, cidx[u]);
-        if (COST != COST_P2P) Nn[u] = rec_load<NF32>(fd.nor_o, cidx[u]);
+        if (F32 && NF32 && COST != COST_P2P) {   // point and normal of the match from one 32-byte record: one sector per gather
+          const float4* pn = fd.pn_o + 2 * (size_t)cidx[u];
+          const float4 a = __ldg(pn), b = __ldg(pn + 1);
+          Q[u].x = a.x; Q[u].y = a.y; Q[u].z = a.z; Nn[u].x = b.x; Nn[u].y = b.y; Nn[u].z = b.z;
+        } else {
+          Q[u] = rec_load<F32>(fd.pts_o, cidx[u]);
+          if (COST != COST_P2P) Nn[u] = rec_load<NF32>(fd.nor_o, cidx[u]);
+        }
       }
 #pragma unroll
     for (int u = 0; u < U; ++u) {

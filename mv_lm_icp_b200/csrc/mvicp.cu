@@ -166,6 +166,16 @@ static unsigned host_workers() {
 
 // common tail of mvicp_set_frames: frame table and identity poses on the device, graph and solver state reset
 static int finish_set_frames(mvicp_ctx* c, int M) {
+  if (c->f32 && c->nor_f32)   // packed point+normal records for the LM gathers (fp32 storage only)
+    for (int f = 0; f < M; ++f) {
+      FrameDev& fr = c->h_frames[f];
+      if (!fr.nor_o) continue;
+      void* d_pn = nullptr;
+      CU(cudaMalloc(&d_pn, sizeof(float4) * 2 * (size_t)fr.n)); c->frame_allocs.push_back(d_pn);
+      pack_pn_kernel<<<(fr.n + 255) / 256, 256, 0, c->stream>>>((const float4*)fr.pts_o, (const float4*)fr.nor_o, fr.n, (float4*)d_pn);
+      c->stats.kernel_launches += 1;
+      fr.pn_o = (const float4*)d_pn;
+    }
   RET(c->d_frames.reserve(sizeof(FrameDev) * M));
   CU(cudaMemcpy(c->d_frames.p, c->h_frames.data(), sizeof(FrameDev) * M, cudaMemcpyHostToDevice));
   RET(c->d_poses.reserve(sizeof(double) * 16 * M));
@@ -209,7 +219,7 @@ static int build_frames_on_device(mvicp_ctx* c, int M, const std::vector<double*
     kd_pack_orig_kernel<F32><<<(n + 255) / 256, 256, 0, c->stream>>>(d_xyz[f], n, d_o);
     if (d_nor[f]) kd_pack_orig_kernel<F32><<<(n + 255) / 256, 256, 0, c->stream>>>(d_nor[f], n, d_n);
     c->stats.kernel_launches += d_nor[f] ? 2 : 1;
-    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n, L, depth, absmax[f]};
+    c->h_frames[f] = FrameDev{d_o, d_n, nullptr, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n, L, depth, absmax[f]};
     ho[f] = ObbDev{(const ObbNode*)d_ob};
   }
   if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
@@ -422,7 +432,7 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     CU(cudaMemcpy(d_fc, builds[f].faces.data(), sizeof(float) * builds[f].faces.size(), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&d_pos, sizeof(int32_t) * n)); c->frame_allocs.push_back(d_pos);
     CU(cudaMemcpy(d_pos, builds[f].pos_of.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
-    c->h_frames[f] = FrameDev{d_o, d_n, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n,
+    c->h_frames[f] = FrameDev{d_o, d_n, nullptr, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n,
                               builds[f].n_leaf_pad, builds[f].depth, builds[f].absmax};
   }
   c->last_lm_iters = 1 << 20;

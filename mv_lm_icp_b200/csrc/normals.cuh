@@ -117,4 +117,11 @@ __global__ void pack_normals_kernel(const double* __restrict__ nor, int n, doubl
   rec[i] = r;
 }
 
+// fp32 storage: point + normal of every point in one 32-byte record (the LM streaming kernel gathers both per match)
+__global__ void pack_pn_kernel(const float4* __restrict__ pts, const float4* __restrict__ nor, int n, float4* __restrict__ pn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pn[2 * (size_t)i] = pts[i]; pn[2 * (size_t)i + 1] = nor[i];
+}
+
 }  // namespace mv

@@ -32,6 +32,7 @@ struct double4a { double x, y, z, w; };   // 32-byte record for the fp64 storage
 struct FrameDev {
   const void* pts_o;     // float4* or double4a*: exact coordinates, caller's order
   const void* nor_o;     // may be null
+  const float4* pn_o;    // fp32 storage with normals: {x y z -, nx ny nz -} per point, 32 B = one sector per LM gather (else null)
   const void* pts_s;     // exact coordinates in tree order, .w = original index (int bits / int64 bits)
   const float4* pts_sf;  // fp32 screening copy in tree order, .w = original index; == pts_s in the fp32 storage mode
   const Box* boxes;      // 2 * n_leaf_pad entries (entry 0 unused), fp32 AABBs rounded outward
