@@ -44,6 +44,7 @@ struct LmWork {
   const int32_t* hb_ptr; const int32_t* hb_row; const int32_t* hb_col; const int32_t* hc_edge; const int32_t* hc_sub; int32_t n_hblocks;
   const int32_t* gb_ptr; const int32_t* gc_edge; const int32_t* gc_side;   // per frame
   const int32_t* rlast; const int32_t* rfirst;   // envelope of the normal matrix: last row touching column j / first column of row r
+  const int32_t* rowbase;                        // skyline storage of the factor: entry (r, c) at Lg[rowbase[r] + c]; [n] = rhs row
   double *H, *g, *Hc, *gc, *scale, *diag, *Lg, *rhs, *step;
   double* poses16;
   int32_t l_in_smem;
@@ -92,7 +93,7 @@ __global__ void lm_init_kernel(LmWork w) {
 }
 
 // ---- dense Cholesky solve --------------------------------------------------------------------------------------
-// L: (n+1) rows of stride ld; rows 0..n-1 hold the lower triangle of the SPD matrix, row n holds the right-hand side
+// L: n+1 rows; rows 0..n-1 hold the lower triangle of the SPD matrix (profile part only), row n holds the right-hand side
 // (treating the rhs as an extra row performs the forward substitution for free).  n is a multiple of 6 (one 6x6 block
 // per free pose), and the factorisation is right-looking over those blocks with a one-block LOOK-AHEAD -- the solve is bound
 // by its dependent chain, not by arithmetic:
@@ -106,14 +107,15 @@ __global__ void lm_init_kernel(LmWork w) {
 // Rows whose profile starts right of the block (rfirst) and rows beyond rlast are structurally zero in the block
 // (envelope of the block-sparse normal matrix; fill-in stays inside each row's profile) and are skipped: only entries
 // inside the row profiles [rfirst[r], r] are ever read or written, the rest of L may hold anything.
-// scratch: >= 2n + 1 ints (row profiles staged in shared memory + the "positive definite so far" flag); dinv: reciprocal
+// L is stored row by row, each row only over its profile (skyline): rowbase[r] + c addresses entry (r, c), rowbase[n] the rhs row.
+// scratch: >= 3n + 2 ints (row profiles and bases staged in shared memory + the "positive definite so far" flag); dinv: reciprocal
 // diagonal of the factor.  The back substitution runs block-wise in one warp.  Solution returned in y[0..n).
-__device__ __forceinline__ void chol_factor_diag(double* L, int ld, int j0, double* dinv, volatile int* s_ok, int lane) {
+__device__ __forceinline__ void chol_factor_diag(double* L, const int32_t* rb, int j0, double* dinv, volatile int* s_ok, int lane) {
   double D[6][6], inv[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int k = 0; k <= i; ++k) D[i][k] = L[(size_t)(j0 + i) * ld + j0 + k];
+    for (int k = 0; k <= i; ++k) D[i][k] = L[rb[j0 + i] + j0 + k];
   bool okb = true;
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -136,23 +138,25 @@ __device__ __forceinline__ void chol_factor_diag(double* L, int ld, int j0, doub
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
-      for (int k = 0; k <= i; ++k) L[(size_t)(j0 + i) * ld + j0 + k] = D[i][k];
+      for (int k = 0; k <= i; ++k) L[rb[j0 + i] + j0 + k] = D[i][k];
       dinv[j0 + i] = inv[i];
     }
   }
 }
 
-__device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* dinv, double* y, const int32_t* __restrict__ rlast,
-                           const int32_t* __restrict__ rfirst) {
+__device__ bool chol_solve(double* L, const int32_t* __restrict__ rowbase, int n, double* scratch, double* dinv, double* y,
+                           const int32_t* __restrict__ rlast, const int32_t* __restrict__ rfirst) {
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   int32_t* s_rfirst = reinterpret_cast<int32_t*>(scratch);
   int32_t* s_rlast = s_rfirst + n;
-  volatile int* s_ok = reinterpret_cast<volatile int*>(s_rlast + n);
+  int32_t* rb = s_rlast + n;                      // row r's entry of column c sits at L[rb[r] + c] (c inside the row's profile)
+  volatile int* s_ok = reinterpret_cast<volatile int*>(rb + n + 1);
   for (int i = tid; i < n; i += T) { s_rfirst[i] = rfirst[i]; s_rlast[i] = rlast[i]; }
+  for (int i = tid; i <= n; i += T) rb[i] = rowbase[i];
   if (tid == 0) *s_ok = 1;
   __syncthreads();
   const int NB = n / 6;
-  if (wid == 0) chol_factor_diag(L, ld, 0, dinv, s_ok, lane);
+  if (wid == 0) chol_factor_diag(L, rb, 0, dinv, s_ok, lane);
   __syncthreads();
   for (int J = 0; J < NB; ++J) {
     if (!*s_ok) return false;                     // uniform: written before the last barrier
@@ -163,13 +167,13 @@ __device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* di
     for (int q = tid; q < nrows; q += T) {
       const int r = (q == nrows - 1) ? n : j0 + 6 + q;
       if (r < n && s_rfirst[r] > j0 + 5) continue;
-      double* row = L + (size_t)r * ld + j0;
+      double* row = L + rb[r] + j0;
       double v[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         double a = row[k];
 #pragma unroll
-        for (int m = 0; m < k; ++m) a -= v[m] * L[(size_t)(j0 + k) * ld + j0 + m];
+        for (int m = 0; m < k; ++m) a -= v[m] * L[rb[j0 + k] + j0 + m];
         v[k] = a * dinv[j0 + k];
       }
 #pragma unroll
@@ -183,28 +187,28 @@ __device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* di
       if (lane < 21 && s_rfirst[b0] <= j0 + 5) {  // (the six rows of a pose share their profile start)
         int i = 0, rem = lane; while (rem > i) { rem -= i + 1; ++i; }   // lane -> (i, k), k <= i
         const int k = rem;
-        double* row = L + (size_t)(b0 + i) * ld; const double* lc = L + (size_t)(b0 + k) * ld + j0;
+        double* row = L + rb[b0 + i]; const double* lc = L + rb[b0 + k] + j0;
         double a = row[b0 + k];
 #pragma unroll
         for (int m = 0; m < 6; ++m) a -= row[j0 + m] * lc[m];
         row[b0 + k] = a;
       }
       __syncwarp();
-      chol_factor_diag(L, ld, b0, dinv, s_ok, lane);
+      chol_factor_diag(L, rb, b0, dinv, s_ok, lane);
     } else {
       const int w0 = next ? 1 : 0, wn = next ? nw - 1 : nw;       // warps that share the remaining rows
       const int qfirst = next ? 6 : 0;                              // rows of the next diagonal block belong to warp 0
       for (int q = qfirst + (wid - w0); q < nrows; q += wn) {
         const int r = (q == nrows - 1) ? n : j0 + 6 + q;
         if (r < n && s_rfirst[r] > j0 + 5) continue;
-        double* row = L + (size_t)r * ld;
+        double* row = L + rb[r];
         double lr[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) lr[k] = row[j0 + k];
         const int cend = min(r, rl);
         for (int c = j0 + 6 + lane; c <= cend; c += 32) {
           if (s_rfirst[c] > j0 + 5) continue;        // row c has nothing in this block: contributes exactly zero
-          const double* lc = L + (size_t)c * ld + j0;
+          const double* lc = L + rb[c] + j0;
           double a = row[c];
 #pragma unroll
           for (int k = 0; k < 6; ++k) a -= lr[k] * lc[k];
@@ -215,7 +219,7 @@ __device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* di
     __syncthreads();
   }
   if (!*s_ok) return false;
-  for (int i = tid; i < n; i += T) y[i] = L[(size_t)n * ld + i];   // forward-substituted rhs
+  for (int i = tid; i < n; i += T) y[i] = L[rb[n] + i];   // forward-substituted rhs
   __syncthreads();
   if (wid == 0) {
     for (int J = NB - 1; J >= 0; --J) {     // L^T x = z, one pose block at a time
@@ -225,7 +229,7 @@ __device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* di
       for (int k = 5; k >= 0; --k) {
         double a = y[j0 + k];
 #pragma unroll
-        for (int m = k + 1; m < 6; ++m) a -= L[(size_t)(j0 + m) * ld + j0 + k] * x[m];
+        for (int m = k + 1; m < 6; ++m) a -= L[rb[j0 + m] + j0 + k] * x[m];
         x[k] = a * dinv[j0 + k];
       }
       __syncwarp();
@@ -234,7 +238,7 @@ __device__ bool chol_solve(double* L, int ld, int n, double* scratch, double* di
       for (int i = s_rfirst[j0] + lane; i < j0; i += 32) {
         double a = y[i];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a -= L[(size_t)(j0 + k) * ld + i] * x[k];
+        for (int k = 0; k < 6; ++k) a -= L[rb[j0 + k] + i] * x[k];
         y[i] = a;
       }
       __syncwarp();
@@ -267,9 +271,9 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     }
     __syncthreads();
   }
-  // dynamic shared memory: [colj (n+1) | dg (n+1) | L (n+1) x (n|1) when it fits]
-  double* colj = smem; double* dg = smem + (S->n + 1);
-  double* L = w.l_in_smem ? smem + 2 * (S->n + 1) : w.Lg;
+  // dynamic shared memory: [scratch 2(n+1) | dg (n+1) | L (skyline) when it fits]
+  double* colj = smem; double* dg = smem + 2 * (S->n + 1);
+  double* L = w.l_in_smem ? smem + 3 * (S->n + 1) : w.Lg;
 
   // ================= 1. gather the per-edge pair matrices (lm_edge_kernel) into Hc, gc; total cost ===================
   // (entries outside the listed blocks are zeroed once by the host when the block structure is built and never written)
@@ -381,18 +385,18 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
         w.diag[j] = fmin(fmax(d, S->opt.min_lm_diagonal), S->opt.max_lm_diagonal);
       }
     __syncthreads();
-    const int ldl = n | 1;   // odd stride: conflict-free column walks
     for (int i = tid >> 5; i < n; i += T >> 5) {          // one warp per row, only the row's profile (see chol_solve)
       const double si = w.scale[i];
+      const int rbi = w.rowbase[i];
       for (int j = w.rfirst[i] + (tid & 31); j <= i; j += 32) {
         double v = si * w.H[(size_t)i * n + j] * w.scale[j];
         if (i == j) { const double ldg = sqrt(w.diag[i] / radius); v += ldg * ldg; }
-        L[(size_t)i * ldl + j] = v;
+        L[rbi + j] = v;
       }
     }
-    for (int j = tid; j < n; j += T) L[(size_t)n * ldl + j] = w.scale[j] * w.g[j];
+    { const int rbn = w.rowbase[n]; for (int j = tid; j < n; j += T) L[rbn + j] = w.scale[j] * w.g[j]; }
     __syncthreads();
-    bool ok = chol_solve(L, ldl, n, colj, dg, w.rhs, w.rlast, w.rfirst);
+    bool ok = chol_solve(L, w.rowbase, n, colj, dg, w.rhs, w.rlast, w.rfirst);
     double bad = 0.0;
     if (ok) for (int j = tid; j < n; j += T) if (!isfinite(w.rhs[j])) bad = 1.0;
     bad = block_sum(bad, red);

@@ -103,7 +103,8 @@ struct mvicp_ctx {
   std::vector<float> h_weight; std::vector<unsigned long long> h_count;
   // LM
   DevBuf d_state, d_x, d_cand, d_Rt, d_K, d_col, d_H, d_g, d_Hc, d_gc, d_scale, d_diag, d_L, d_rhs, d_step,
-      d_eout, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst, d_gen;
+      d_eout, d_hb_ptr, d_hb_row, d_hb_col, d_hc_edge, d_hc_sub, d_gb_ptr, d_gc_edge, d_gc_side, d_posegather, d_rlast, d_rfirst, d_rowbase, d_gen;
+  int64_t l_size = 0;          // doubles of the factor's skyline storage (row profiles + rhs row)
   int n_free = 0, n_hblocks = 0;
   std::vector<int32_t> h_col;
   void* h_state = nullptr;     // pinned staging of LmState
@@ -355,7 +356,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_gen, &c->d_obb, &c->d_single, &c->d_tile_count, &c->d_tile_off, &c->d_edge_off, &c->d_recs};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_rowbase, &c->d_gen, &c->d_obb, &c->d_single, &c->d_tile_count, &c->d_tile_off, &c->d_edge_off, &c->d_recs};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -792,7 +793,6 @@ static int prepare_lm(mvicp_ctx* c, int n) {
   RET(c->d_Rt.reserve(sizeof(Rt) * M)); RET(c->d_K.reserve(sizeof(double) * 36 * M));
   RET(c->d_col.reserve(sizeof(int32_t) * M));
   RET(c->d_H.reserve(sizeof(double) * n * n)); RET(c->d_Hc.reserve(sizeof(double) * n * n));
-  RET(c->d_L.reserve(sizeof(double) * (size_t)(n + 1) * (n | 1)));
   RET(c->d_g.reserve(sizeof(double) * n)); RET(c->d_gc.reserve(sizeof(double) * n)); RET(c->d_scale.reserve(sizeof(double) * n));
   RET(c->d_diag.reserve(sizeof(double) * n)); RET(c->d_rhs.reserve(sizeof(double) * n)); RET(c->d_step.reserve(sizeof(double) * n));
   RET(c->d_eout.reserve(sizeof(double) * EOUT * E));
@@ -898,6 +898,14 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
     RET(up(c->d_hc_sub, hc_sub)); RET(up(c->d_gb_ptr, gb_ptr)); RET(up(c->d_gc_edge, gc_edge)); RET(up(c->d_gc_side, gc_side));
     RET(up(c->d_col, c->h_col));
     RET(up(c->d_rlast, rlast)); RET(up(c->d_rfirst, rfirst));
+    // skyline storage of the Cholesky factor: row r keeps columns rfirst[r]..r, the rhs row all n
+    std::vector<int32_t> rowbase(n + 1); int64_t at = 0;
+    for (int r = 0; r < n; ++r) { rowbase[r] = (int32_t)(at - rfirst[r]); at += r - rfirst[r] + 1; }
+    rowbase[n] = (int32_t)at; at += n;
+    if (at > INT32_MAX) return fail(MVICP_ERR_INVALID, "normal matrix too large");
+    c->l_size = at;
+    RET(c->d_L.reserve(sizeof(double) * (size_t)at));
+    RET(up(c->d_rowbase, rowbase));
     // the step kernel writes only the listed blocks of the dense normal matrix; everything else stays zero from here
     CU(cudaMemsetAsync(c->d_H.p, 0, sizeof(double) * (size_t)n * n, c->stream));
     CU(cudaMemsetAsync(c->d_Hc.p, 0, sizeof(double) * (size_t)n * n, c->stream));
@@ -921,13 +929,13 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   w.col = c->d_col.as<int32_t>();
   w.hb_ptr = c->d_hb_ptr.as<int32_t>(); w.hb_row = c->d_hb_row.as<int32_t>(); w.hb_col = c->d_hb_col.as<int32_t>();
   w.hc_edge = c->d_hc_edge.as<int32_t>(); w.hc_sub = c->d_hc_sub.as<int32_t>(); w.n_hblocks = c->n_hblocks;
-  w.rlast = c->d_rlast.as<int32_t>(); w.rfirst = c->d_rfirst.as<int32_t>();
+  w.rlast = c->d_rlast.as<int32_t>(); w.rfirst = c->d_rfirst.as<int32_t>(); w.rowbase = c->d_rowbase.as<int32_t>();
   w.gb_ptr = c->d_gb_ptr.as<int32_t>(); w.gc_edge = c->d_gc_edge.as<int32_t>(); w.gc_side = c->d_gc_side.as<int32_t>();
   w.H = c->d_H.as<double>(); w.g = c->d_g.as<double>(); w.Hc = c->d_Hc.as<double>(); w.gc = c->d_gc.as<double>();
   w.scale = c->d_scale.as<double>(); w.diag = c->d_diag.as<double>(); w.Lg = c->d_L.as<double>(); w.rhs = c->d_rhs.as<double>();
   w.step = c->d_step.as<double>(); w.poses16 = c->d_poses.as<double>();
-  const size_t l_bytes = sizeof(double) * (size_t)(n + 1) * (n | 1);
-  const size_t vec_bytes = sizeof(double) * 2 * (size_t)(n + 1);
+  const size_t l_bytes = sizeof(double) * (size_t)c->l_size;
+  const size_t vec_bytes = sizeof(double) * 3 * (size_t)(n + 1);
   w.l_in_smem = (l_bytes + vec_bytes) <= 220 * 1024 ? 1 : 0;
   const size_t dyn = vec_bytes + (w.l_in_smem ? l_bytes : 0);
   CU(cudaFuncSetAttribute(lm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

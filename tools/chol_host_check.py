@@ -45,12 +45,13 @@ int main() {
   for (int j = 0; j < n; ++j) rlast[j] = j;
   for (int r = 0; r < n; ++r) for (int j = rfirst[r]; j <= r; ++j) rlast[j] = std::max(rlast[j], r);
   for (int j = 1; j < n; ++j) rlast[j] = std::max(rlast[j], rlast[j - 1]);
-  std::vector<double> L((size_t)(n + 1) * ld, NAN), scratch(n + 1), dinv(n + 1), y(n);
+  std::vector<double> L((size_t)(n + 1) * ld, NAN), scratch(2 * (n + 1)), dinv(n + 1), y(n);
+  std::vector<int> rowbase(n + 1); for (int r = 0; r <= n; ++r) rowbase[r] = r * ld;   // dense rows here; the engine packs the profiles
   for (int i = 0; i < n; ++i) for (int j = rfirst[i]; j <= i; ++j) L[(size_t)i * ld + j] = H[(size_t)i * n + j];
   for (int j = 0; j < n; ++j) L[(size_t)n * ld + j] = g[j];
   std::barrier<> bar(512); g_bar = &bar; for (int w = 0; w < 16; ++w) g_wbar.push_back(new std::barrier<>(32));
   std::vector<std::thread> th; std::vector<int> oks(512);
-  for (int t = 0; t < 512; ++t) th.emplace_back([&, t]() { threadIdx.x = t; oks[t] = chol_solve(L.data(), ld, n, scratch.data(), dinv.data(), y.data(), rlast.data(), rfirst.data()); });
+  for (int t = 0; t < 512; ++t) th.emplace_back([&, t]() { threadIdx.x = t; oks[t] = chol_solve(L.data(), rowbase.data(), n, scratch.data(), dinv.data(), y.data(), rlast.data(), rfirst.data()); });
   for (auto& t : th) t.join();
   double maxr = 0, maxg = 0;
   for (int i = 0; i < n; ++i) { double s = 0; for (int j = 0; j < n; ++j) s += H[(size_t)i * n + j] * y[j]; maxr = std::max(maxr, std::fabs(s - g[i])); maxg = std::max(maxg, std::fabs(g[i])); }
