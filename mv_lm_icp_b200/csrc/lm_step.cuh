@@ -294,10 +294,10 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     w.gc[w.col[f] + i] = s;
   }
   __syncthreads();
+  // total cost: edges summed in a fixed order (thread t takes edges t, t + T, ...; then the block tree) -- the same on every rank
   double eval_cost = 0.0;
-  if (tid == 0) { for (int e = 0; e < E; ++e) eval_cost += w.eout[(size_t)EOUT * e + 156]; red[33] = eval_cost; }
-  __syncthreads();
-  eval_cost = red[33];
+  for (int e = tid; e < E; e += T) eval_cost += w.eout[(size_t)EOUT * e + 156];
+  eval_cost = block_sum(eval_cost, red);
 
   // ================= 2. accept / reject / terminate =================================================
   bool take = false;    // the evaluation point becomes the accepted point
