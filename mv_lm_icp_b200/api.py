@@ -17,6 +17,7 @@ TERMINATION = ["FUNCTION_TOLERANCE", "GRADIENT_TOLERANCE", "PARAMETER_TOLERANCE"
 FLAG_NO_SEED = 1
 FLAG_NCCL_ONLY = 2
 FLAG_HOST_BUILD = 4
+FLAG_NO_ADJ = 8
 FLAG_NO_OBB = 16
 
 

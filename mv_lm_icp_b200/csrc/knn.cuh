@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <limits.h>
+#include "adjacency.h"
 #include "types.cuh"
 
 namespace mv {
@@ -129,10 +130,33 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_le
     leaf_node = L + start_leaf;
 #pragma unroll
     for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, start_leaf, sub, s);
-    // a stale guess (the poses moved a lot since it was made) leaves a loose bound, and everything inside that ball
-    // would be visited on the way up: if the guess is further than a few leaf sizes, descend greedily instead
     const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
     const float4 u = __ldg(b), v = __ldg(b + 1);
+    if (fd.adj) {
+      // Inside the start leaf's reach (adjacency.h) the answer lies in this leaf or in one of its listed neighbours: test their
+      // boxes, scan the ones that can still hold a closer point -- no walk up the ancestors, no descents.
+      const int32_t* ap = fd.adj + (size_t)ADJ_SLOTS * start_leaf;
+      const int2 hd = __ldg(reinterpret_cast<const int2*>(ap));
+      const float ex0 = fmaxf(fmaxf(u.x - s.fx, s.fx - u.w), 0.f), ey0 = fmaxf(fmaxf(u.y - s.fy, s.fy - v.x), 0.f), ez0 = fmaxf(fmaxf(u.z - s.fz, s.fz - v.y), 0.f);
+      const float e2 = fmaf(ez0, ez0, fmaf(ey0, ey0, ex0 * ex0));
+      // e + r <= R_S, every operation rounded up; the error of e (query and box in fp32) is inside the allowance that bound32 carries
+      if (__fadd_ru(sqrt_upper(e2), sqrt_upper(s.bound32)) <= __int_as_float(hd.x)) {
+        unsigned todo = 0u;
+        for (int i = 0; i < hd.y; ++i) {
+          const int t = __ldg(ap + 2 + i);
+          if (box_lb32(fd.boxes, L + t, s) <= s.bound32) todo |= 1u << i;
+        }
+        while (todo) {
+          const int i = __ffs(todo) - 1; todo &= todo - 1u;
+          const int t = __ldg(ap + 2 + i);
+#pragma unroll
+          for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, t, sub, s);
+        }
+        return;
+      }
+    }
+    // a stale guess (the poses moved a lot since it was made) leaves a loose bound, and everything inside that ball
+    // would be visited on the way up: if the guess is further than a few leaf sizes, descend greedily instead
     const float ex = u.w - u.x, ey = v.x - u.y, ez = v.y - u.z;                 // extents of the leaf
     if (s.bound32 > 16.0f * fmaf(ez, ez, fmaf(ey, ey, ex * ex))) start_leaf = -1;
   }

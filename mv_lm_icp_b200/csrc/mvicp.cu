@@ -206,21 +206,22 @@ static int build_frames_on_device(mvicp_ctx* c, int M, const std::vector<double*
     int L = 1; while (L < n_leaf) L <<= 1;
     int depth = 0; while ((1 << depth) < L) ++depth;
     const int n_pad = (int)(n_leaf * LEAF);
-    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr, *d_fc = nullptr, *d_ob = nullptr;
+    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr, *d_fc = nullptr, *d_ob = nullptr, *d_adj = nullptr;
     auto grab = [&](void** p, size_t bytes) { if (err == cudaSuccess) { err = cudaMalloc(p, bytes); if (err == cudaSuccess) c->frame_allocs.push_back(*p); } };
     grab(&d_o, rec * (size_t)n); grab(&d_s, rec * (size_t)n_pad); grab(&d_b, sizeof(Box) * 2 * (size_t)L); grab(&d_fc, sizeof(float) * 2 * (size_t)L);
-    grab(&d_pos, sizeof(int32_t) * (size_t)n);
+    grab(&d_pos, sizeof(int32_t) * (size_t)n); grab(&d_adj, sizeof(int32_t) * ADJ_SLOTS * (size_t)L);
     if (F32) d_sf = d_s; else grab(&d_sf, sizeof(float4) * (size_t)n_pad);
     if (d_nor[f]) grab(&d_n, rec * (size_t)n);
     if (want_obb) grab(&d_ob, sizeof(ObbNode) * 2 * (size_t)L);
     if (err != cudaSuccess) break;
     const KdGeom g{n, L, depth};
-    err = kd_build_device<F32>(c->stream, S, d_xyz[f], g, d_s, (float4*)d_sf, (int32_t*)d_pos, (Box*)d_b, (float*)d_fc, (ObbNode*)d_ob,
+    err = kd_build_device<F32>(c->stream, S, d_xyz[f], g, d_s, (float4*)d_sf, (int32_t*)d_pos, (Box*)d_b, (float*)d_fc, (int32_t*)d_adj, (ObbNode*)d_ob,
                                &c->stats.kernel_launches);
     kd_pack_orig_kernel<F32><<<(n + 255) / 256, 256, 0, c->stream>>>(d_xyz[f], n, d_o);
     if (d_nor[f]) kd_pack_orig_kernel<F32><<<(n + 255) / 256, 256, 0, c->stream>>>(d_nor[f], n, d_n);
     c->stats.kernel_launches += d_nor[f] ? 2 : 1;
-    c->h_frames[f] = FrameDev{d_o, d_n, nullptr, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n, L, depth, absmax[f]};
+    c->h_frames[f] = FrameDev{d_o, d_n, nullptr, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos,
+                              (c->flags & MVICP_FLAG_NO_ADJ) ? nullptr : (const int32_t*)d_adj, (int32_t)n, L, depth, absmax[f]};
     ho[f] = ObbDev{(const ObbNode*)d_ob};
   }
   if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
@@ -403,7 +404,7 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
   std::vector<char> stage;
   for (int f = 0; f < M; ++f) {
     const int64_t n = n_pts[f];
-    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr, *d_fc = nullptr;
+    void *d_o = nullptr, *d_n = nullptr, *d_s = nullptr, *d_b = nullptr, *d_sf = nullptr, *d_pos = nullptr, *d_fc = nullptr, *d_adj = nullptr;
     CU(cudaMalloc(&d_o, rec * n)); c->frame_allocs.push_back(d_o);
     const int64_t n_pad = ((n + LEAF - 1) / LEAF) * LEAF;   // tree-order arrays are padded to whole leaves with +inf points
     CU(cudaMalloc(&d_s, rec * n_pad)); c->frame_allocs.push_back(d_s);
@@ -433,8 +434,10 @@ int mvicp_set_frames(mvicp_ctx* c, int32_t M, const double* const* pts, const do
     CU(cudaMemcpy(d_fc, builds[f].faces.data(), sizeof(float) * builds[f].faces.size(), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&d_pos, sizeof(int32_t) * n)); c->frame_allocs.push_back(d_pos);
     CU(cudaMemcpy(d_pos, builds[f].pos_of.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
-    c->h_frames[f] = FrameDev{d_o, d_n, nullptr, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos, (int32_t)n,
-                              builds[f].n_leaf_pad, builds[f].depth, builds[f].absmax};
+    CU(cudaMalloc(&d_adj, sizeof(int32_t) * builds[f].adj.size())); c->frame_allocs.push_back(d_adj);
+    CU(cudaMemcpy(d_adj, builds[f].adj.data(), sizeof(int32_t) * builds[f].adj.size(), cudaMemcpyHostToDevice));
+    c->h_frames[f] = FrameDev{d_o, d_n, nullptr, d_s, (const float4*)d_sf, (const Box*)d_b, (const float*)d_fc, (const int32_t*)d_pos,
+                              (c->flags & MVICP_FLAG_NO_ADJ) ? nullptr : (const int32_t*)d_adj, (int32_t)n, builds[f].n_leaf_pad, builds[f].depth, builds[f].absmax};
   }
   c->last_lm_iters = 1 << 20;
   if (!(c->flags & MVICP_FLAG_NO_OBB)) {    // hybrid oriented boxes: a second node array for the far rounds (far.cuh)

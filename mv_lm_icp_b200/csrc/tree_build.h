@@ -7,6 +7,7 @@
 #include <cstring>
 #include <numeric>
 #include <vector>
+#include "adjacency.h"
 #include "types.cuh"
 
 using namespace mv;
@@ -19,6 +20,7 @@ struct HostFrameBuild {
   std::vector<int32_t> pos_of;     // original index -> tree position
   std::vector<Box> boxes;
   std::vector<float> faces;        // split-plane bound per node (axis in the low 2 mantissa bits)
+  std::vector<int32_t> adj;        // per leaf slot ADJ_SLOTS ints: reach, count, neighbouring leaves (adjacency.h)
   int n_leaf_pad = 1, depth = 0;
   float absmax = 0.f;
 };
@@ -94,6 +96,8 @@ static void build_frame(const double* pts, int64_t n, HostFrameBuild& out) {
       out.faces[i] = ff;
     }
   }
+  out.adj.assign((size_t)ADJ_SLOTS * L, 0);
+  for (int l = 0; l < L; ++l) adj_build_leaf(out.boxes.data(), L, (int)n_leaf, l, out.adj.data() + (size_t)ADJ_SLOTS * l);
 }
 
 

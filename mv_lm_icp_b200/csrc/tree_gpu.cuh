@@ -20,6 +20,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "adjacency.h"
 #include "far.cuh"
 #include "types.cuh"
 
@@ -202,6 +203,15 @@ __global__ void kd_boxface_kernel(int L, const double* __restrict__ dbox, const 
   faces[i] = ff;
 }
 
+// neighbour list and reach of every leaf (adjacency.h)
+__global__ void kd_adj_kernel(const Box* __restrict__ boxes, int L, int n_leaf, int32_t* __restrict__ adj) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  int32_t o[ADJ_SLOTS];
+  adj_build_leaf(boxes, L, n_leaf, l, o);
+  for (int i = 0; i < ADJ_SLOTS; ++i) adj[(size_t)ADJ_SLOTS * l + i] = o[i];
+}
+
 // hybrid oriented boxes (tree_build.h:build_obb, same rules): per node the box of the coordinate axes, or -- nodes of at most
 // OBB_PCA_LEAVES leaves whose principal-axes box is clearly smaller -- the box of the principal axes of its points
 constexpr int OBB_PCA_LEAVES = 8;
@@ -314,7 +324,7 @@ struct KdScratch {
 // order_out: tree position -> original index.  Returns the first CUDA error.
 template <bool F32>
 static cudaError_t kd_build_device(cudaStream_t st, KdScratch& S, const double* d_xyz, KdGeom g, void* pts_s, float4* pts_sf, int32_t* pos_of,
-                                   Box* boxes, float* faces, ObbNode* obb /*nullable*/, int64_t* launches) {
+                                   Box* boxes, float* faces, int32_t* adj, ObbNode* obb /*nullable*/, int64_t* launches) {
   const int n = g.n, L = g.L, T = 256;
   cudaError_t e = S.reserve((size_t)n, (size_t)L);
   if (e != cudaSuccess) return e;
@@ -340,8 +350,9 @@ static cudaError_t kd_build_device(cudaStream_t st, KdScratch& S, const double* 
   kd_leaf_kernel<<<(L + T - 1) / T, T, 0, st>>>(d_xyz, order, g, S.dbox, obb ? S.mom : nullptr);
   for (int first = L / 2; first >= 1; first /= 2) kd_merge_kernel<<<(first + T - 1) / T, T, 0, st>>>(first, S.dbox, obb ? S.mom : nullptr);
   kd_boxface_kernel<<<(2 * L + T - 1) / T, T, 0, st>>>(L, S.dbox, S.axis_of, boxes, faces);
+  kd_adj_kernel<<<(L + 63) / 64, 64, 0, st>>>(boxes, L, (n + LEAF - 1) / LEAF, adj);
   if (obb) kd_obb_kernel<<<(2 * L + T - 1) / T, T, 0, st>>>(d_xyz, order, g, S.dbox, S.mom, obb);
-  *launches += 3 + g.depth + (obb ? 1 : 0);
+  *launches += 4 + g.depth + (obb ? 1 : 0);
   return cudaGetLastError();
 }
 

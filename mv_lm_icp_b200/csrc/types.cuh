@@ -38,6 +38,7 @@ struct FrameDev {
   const Box* boxes;      // 2 * n_leaf_pad entries (entry 0 unused), fp32 AABBs rounded outward
   const float* faces;    // per node: one-sided bound along the parent's split axis, axis in the low 2 mantissa bits
   const int32_t* pos_of; // original index -> position in tree order (seed -> leaf)
+  const int32_t* adj;    // per leaf 16 ints: reach, count, neighbouring leaves (adjacency.h); may be null
   int32_t n;             // points
   int32_t n_leaf_pad;    // power of two >= ceil(n / LEAF)
   int32_t depth;         // log2(n_leaf_pad)

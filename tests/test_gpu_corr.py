@@ -5,7 +5,7 @@ import pytest
 
 from helpers import oracle_correspond, scene
 from mv_lm_icp_b200 import Engine, synth
-from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_OBB, FLAG_NO_SEED
+from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED
 
 pytestmark = pytest.mark.gpu
 
@@ -45,13 +45,15 @@ def test_synthetic_bit_exact(oracle, n_views, n_points, cfg):
     eng.close()
 
 
-SCHEDULES = (FLAG_NO_SEED, FLAG_NO_OBB, FLAG_NO_OBB | FLAG_NO_SEED, FLAG_HOST_BUILD, FLAG_HOST_BUILD | FLAG_NO_SEED, FLAG_HOST_BUILD | FLAG_NO_OBB)
+SCHEDULES = (FLAG_NO_SEED, FLAG_NO_OBB, FLAG_NO_OBB | FLAG_NO_SEED, FLAG_HOST_BUILD, FLAG_HOST_BUILD | FLAG_NO_SEED, FLAG_HOST_BUILD | FLAG_NO_OBB,
+             FLAG_NO_ADJ, FLAG_NO_ADJ | FLAG_HOST_BUILD, FLAG_NO_ADJ | FLAG_NO_OBB | FLAG_NO_SEED)
 
 
 def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=()):
-    """Seeded / unseeded, with / without the oriented node boxes that the far rounds search (far.cuh), search trees built on the
-    device (tree_gpu.cuh, default) or on the host (tree_build.h): the same exact search, bit-identical output.  Odd cloud sizes
-    leave partially filled warps and padding leaves in play."""
+    """Seeded / unseeded, with / without the per-leaf neighbour lists that let a seeded query skip the tree walk (adjacency.h), with /
+    without the oriented node boxes that the far rounds search (far.cuh), search trees built on the device (tree_gpu.cuh, default)
+    or on the host (tree_build.h): the same exact search, bit-identical output.  Odd cloud sizes leave partially filled warps and
+    padding leaves in play."""
     sc = scene(4, 5003, 21)
     edges = synth.ring_edges(4, 2)
     res = []

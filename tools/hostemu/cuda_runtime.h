@@ -196,6 +196,7 @@ inline float __double2float_rn(double a) { return (float)a; }
 inline float hs_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
 inline float __double2float_ru(double a) { return hs_up(a); }
 inline float __fsqrt_ru(float a) { return std::nextafterf(hs_up(std::sqrt((double)a)), INFINITY); }
+inline float __fadd_ru(float a, float b) { return hs_up((double)a + (double)b); }
 inline float __fmul_ru(float a, float b) { return hs_up((double)a * (double)b); }
 inline float __fmaf_ru(float a, float b, float c) { return std::nextafterf(hs_up((double)a * (double)b + (double)c), INFINITY); }
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }

@@ -92,3 +92,47 @@ int sim_query(void* h, const double* q, int start_leaf, int reseed, int64_t* cou
   return bi;
 }
 }
+
+// steady-state anatomy of one seeded query (development aid): after the start leaf's scan, which ancestor levels survive the
+// split-plane pre-filter (bit l of *plane_mask), which of those also survive the box test (*box_mask), and the per-leaf
+// "reach" table idea: the smallest level L* such that every level >= L* is pruned by the distance from the LEAF'S BOX to the
+// split planes alone (no per-query work) given the query's reach r + e (returned in *lstar).
+extern "C" int sim_anatomy(void* h, const double* q, int start_leaf, unsigned* plane_mask, unsigned* box_mask, int* lstar) {
+  Sim& s = *(Sim*)h; const HostFrameBuild& t = s.b; const int L = t.n_leaf_pad;
+  const float fx = (float)q[0], fy = (float)q[1], fz = (float)q[2];
+  double best = INFINITY; int bi = -1;
+  for (int j = 0; j < LEAF; ++j) {
+    const int64_t pos = (int64_t)start_leaf * LEAF + j; if (pos >= s.n) break;
+    const double ex = q[0] - (double)s.px[pos], ey = q[1] - (double)s.py[pos], ez = q[2] - (double)s.pz[pos];
+    const double d = ex * ex + ey * ey + ez * ez; if (d < best) { best = d; bi = s.pi[pos]; }
+  }
+  const float bound = (float)((std::sqrt(best) + 1e-6) * (std::sqrt(best) + 1e-6) * 1.000001);
+  const int leaf_node = L + start_leaf;
+  const Box& lb = t.boxes[leaf_node];
+  const float qa3[3] = {fx, fy, fz};
+  float emax = 0.f; for (int a = 0; a < 3; ++a) emax = std::fmax(emax, std::fmax(lb.lo[a] - qa3[a], qa3[a] - lb.hi[a]));
+  emax = std::fmax(emax, 0.f);
+  *plane_mask = 0; *box_mask = 0; *lstar = 0;
+  float mmin = INFINITY;   // running min over levels >= l of the leaf-box-to-plane gap, scanned from the top level down
+  int ls = t.depth;
+  for (int l = t.depth - 1; l >= 0; --l) {
+    const int sib = (leaf_node >> l) ^ 1;
+    const float face = t.faces[sib]; uint32_t bits; std::memcpy(&bits, &face, 4); const int axis = bits & 3;
+    const float g = (sib & 1) ? face - lb.hi[axis] : lb.lo[axis] - face;   // gap between the leaf's box and the plane
+    mmin = std::fmin(mmin, g);
+    const float reach = mmin - emax;
+    if (reach > 0.f && reach * reach > bound) ls = l;   // every level >= l is out of reach
+    const float dpl = (sib & 1) ? face - qa3[axis] : qa3[axis] - face;
+    if (dpl > 0.f && dpl * dpl > bound) continue;
+    *plane_mask |= 1u << l;
+    if (lb32(t.boxes[sib], fx, fy, fz) <= bound) *box_mask |= 1u << l;
+  }
+  // ls as computed is the smallest l for which the suffix [l, depth) is prunable by the table (suffix minima are monotone)
+  *lstar = ls;
+  return bi;
+}
+extern "C" void sim_leaf_boxes(void* h, float* out /*[L][6]*/) {
+  Sim& s = *(Sim*)h; const int L = s.b.n_leaf_pad;
+  for (int l = 0; l < L; ++l) for (int a = 0; a < 3; ++a) { out[6 * l + a] = s.b.boxes[L + l].lo[a]; out[6 * l + 3 + a] = s.b.boxes[L + l].hi[a]; }
+}
+extern "C" int sim_nleafpad(void* h) { return ((Sim*)h)->b.n_leaf_pad; }
