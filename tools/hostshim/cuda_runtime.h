@@ -29,6 +29,8 @@ static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline float hs_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
 static inline float __double2float_ru(double a) { return hs_up(a); }
 static inline float __fsqrt_ru(float a) { return std::nextafterf(hs_up(std::sqrt((double)a)), INFINITY); }
+static inline float __fadd_ru(float a, float b) { return hs_up((double)a + (double)b); }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline float __fmul_ru(float a, float b) { return hs_up((double)a * (double)b); }
 static inline float __fmaf_ru(float a, float b, float c) { return std::nextafterf(hs_up((double)a * (double)b + (double)c), INFINITY); }
 static inline void __syncthreads() {}

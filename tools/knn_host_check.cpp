@@ -1,5 +1,5 @@
 // tools/knn_host_check.cpp -- compiles the engine's own csrc/knn.cuh + tree_build.h with g++ (tools/hostshim) and runs the
-// SEARCH TEXT (nn_query_init / nn_search / nn_search_warp with a one-lane warp) on the host against a brute force in the
+// SEARCH TEXT (nn_query_init / nn_search, with and without the per-leaf neighbour lists of adjacency.h) on the host against a brute force in the
 // reference's operation order, or (--file <bin>) against a golden answer.  Usage: knn_host_check <n_points> <n_queries> <seed> <mode>   mode 0: fp32-exact coordinates
 // (fp32 storage), 1: arbitrary doubles (fp64 records + rounded fp32 screening copy).  Exit code 0 = all queries exact.
 #include <cstdio>
@@ -46,7 +46,8 @@ static int run_file(const char* path) {
       for (int sched = 0; sched < 2; ++sched) {
         NNQuery s2; nn_query_init(s2, q[3 * i], q[3 * i + 1], q[3 * i + 2], F.fd.absmax);
         const int start_leaf = pass == 0 ? -1 : F.hb.pos_of[prev[i]] / LEAF;
-        if (sched == 0) nn_search<false, NNQuery>(F.fd, s2, start_leaf); else nn_search_warp<false>(F.fd, s2, start_leaf, true);
+        FrameDev fdx = F.fd; fdx.adj = sched == 0 ? F.hb.adj.data() : nullptr;   // with / without the neighbour lists
+        nn_search<false, NNQuery>(fdx, s2, start_leaf);
         if (s2.bi != wi[i] || s2.best != wd[i]) { if (++bad < 10) std::printf("MISMATCH q %lld pass %d sched %d: got (%d, %.17g) want (%d, %.17g)\n", (long long)i, pass, sched, s2.bi, s2.best, wi[i], wd[i]); }
         prev[i] = s2.bi;
       }
@@ -96,7 +97,8 @@ template <bool F32> static int run(int n, int nq, unsigned seed) {
       const int start_leaf = sk == 0 ? -1 : (sk == 1 ? hb.pos_of[bi] / LEAF : (int)(rng() % ((n + LEAF - 1) / LEAF)));
       for (int sched = 0; sched < 2; ++sched) {
         NNQuery s2; nn_query_init(s2, q[0], q[1], q[2], fd.absmax);
-        if (sched == 0) nn_search<F32, NNQuery>(fd, s2, start_leaf); else nn_search_warp<F32>(fd, s2, start_leaf, true);
+        FrameDev fdx = fd; fdx.adj = sched == 0 ? hb.adj.data() : nullptr;
+        nn_search<F32, NNQuery>(fdx, s2, start_leaf);
         if (s2.bi != bi || s2.best != best) {
           if (++bad < 10) std::printf("MISMATCH q %d kind %d seed-kind %d sched %d: got (%d, %.17g) want (%d, %.17g)\n", qi, kind, sk, sched, s2.bi, s2.best, bi, best);
         }
