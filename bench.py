@@ -86,7 +86,12 @@ def cpu_threads():
 def _gen_view(a):
     from mv_lm_icp_b200 import synth
     v, views, points, cid = a
-    p, n, P = synth.make_view(v, views, points, 0xB200 + 1000 * cid + v)
+    try:   # one BLAS thread per worker: the pool already fills the CPUs this process may use
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            p, n, P = synth.make_view(v, views, points, 0xB200 + 1000 * cid + v)
+    except ImportError:
+        p, n, P = synth.make_view(v, views, points, 0xB200 + 1000 * cid + v)
     return v, p, n
 
 
