@@ -376,11 +376,9 @@ constexpr int GBLK = 96;   // stride of a general partial: 78 (upper 12x12) | 12
 __device__ __forceinline__ int u12(int i, int j) { return i * 12 - (i * (i - 1)) / 2 + (j - i); }
 
 template <bool F32, bool NF32, int COST, int PASS>
-__global__ void __launch_bounds__(EVAL_THREADS)
-lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
+__device__ __forceinline__ void lm_eval_general_pass(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
                        int tile_len, const int32_t* __restrict__ corr, const FrameGen* __restrict__ frame_gen,
-                       const float* __restrict__ weight, int robust, double* __restrict__ partial, const int* __restrict__ done_flag) {
-  if (*done_flag) return;
+                       const float* __restrict__ weight, int robust, double* __restrict__ partial) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ FrameGen gs, gk;
@@ -464,6 +462,18 @@ lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __res
     else { int a = 0, rem = i; while (rem >= 6 - a) { rem -= 6 - a; ++a; } dst = u12(6 + a, 6 + a + rem); }
     partial[(size_t)blockIdx.x * GBLK + dst] = v;
   }
+}
+
+// the three passes in one launch: blockIdx.y = pass (each writes its own part of the tile's partial)
+template <bool F32, bool NF32, int COST>
+__global__ void __launch_bounds__(EVAL_THREADS)
+lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
+                       int tile_len, const int32_t* __restrict__ corr, const FrameGen* __restrict__ frame_gen,
+                       const float* __restrict__ weight, int robust, double* __restrict__ partial, const int* __restrict__ done_flag) {
+  if (*done_flag) return;
+  if (blockIdx.y == 0) lm_eval_general_pass<F32, NF32, COST, 0>(frames, edges, tiles, tile_len, corr, frame_gen, weight, robust, partial);
+  else if (blockIdx.y == 1) lm_eval_general_pass<F32, NF32, COST, 1>(frames, edges, tiles, tile_len, corr, frame_gen, weight, robust, partial);
+  else lm_eval_general_pass<F32, NF32, COST, 2>(frames, edges, tiles, tile_len, corr, frame_gen, weight, robust, partial);
 }
 
 // general-path counterpart of lm_edge_kernel: the partials already are the pair matrix in the parameterisation tangent

@@ -819,16 +819,14 @@ template <bool F32> static void launch_eval(mvicp_ctx* c, int cost, int robust, 
 template <bool F32> static void launch_eval_general(mvicp_ctx* c, int cost, int robust, const int* done_flag) {
   const int nt = c->n_eval_tiles;
   if (!nt) return;
-#define MV_EVALG(COSTK, PASSK)                                                                                   \
-  if (F32 && c->nor_f32) lm_eval_general_kernel<F32, F32, COSTK, PASSK><<<nt, EVAL_THREADS, 0, c->stream>>>(     \
+#define MV_EVALG(COSTK)                                                                                          \
+  if (F32 && c->nor_f32) lm_eval_general_kernel<F32, F32, COSTK><<<dim3(nt, 3), EVAL_THREADS, 0, c->stream>>>(        \
       c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
       c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag); \
-  else lm_eval_general_kernel<F32, false, COSTK, PASSK><<<nt, EVAL_THREADS, 0, c->stream>>>(                     \
+  else lm_eval_general_kernel<F32, false, COSTK><<<dim3(nt, 3), EVAL_THREADS, 0, c->stream>>>(                        \
       c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
       c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag)
-#define MV_EVALG3(COSTK) { MV_EVALG(COSTK, 0); MV_EVALG(COSTK, 1); MV_EVALG(COSTK, 2); }
-  if (cost == COST_P2P) MV_EVALG3(COST_P2P) else if (cost == COST_P2PLANE) MV_EVALG3(COST_P2PLANE) else MV_EVALG3(COST_MIXED)
-#undef MV_EVALG3
+  if (cost == COST_P2P) { MV_EVALG(COST_P2P); } else if (cost == COST_P2PLANE) { MV_EVALG(COST_P2PLANE); } else { MV_EVALG(COST_MIXED); }
 #undef MV_EVALG
 }
 extern "C" {
