@@ -315,10 +315,24 @@ def run_reference(args, cfg):
 # ======================================================================================================
 # GPU arm
 # ======================================================================================================
+def _file_barrier(cid, cfg, timeout_s=3600):
+    """Ranks generate disjoint shares of the scene BEFORE torch / NCCL / CUDA are initialised (the generator forks a process
+    pool); they meet again when every view's file exists (files appear by atomic rename)."""
+    def wait():
+        base = f"/tmp/mvicp_scene_c{cid}_{cfg['views']}x{cfg['points']}"
+        t0 = time.time()
+        while not all(os.path.exists(f"{base}_v{v}.npz") for v in range(cfg["views"])):
+            if time.time() - t0 > timeout_s:
+                raise RuntimeError("scene generation: another rank never delivered its views")
+            time.sleep(0.2)
+    return wait
+
+
 def run_ours(args, cfg):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    sc = load_scene(args.config, cfg, rank, world, _file_barrier(args.config, cfg) if (world > 1 and args.config != "real") else None)
     import torch
     import mv_lm_icp_b200 as mv
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -327,7 +341,6 @@ def run_ours(args, cfg):
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
 
-    sc = load_scene(args.config, cfg, rank, world, (lambda: dist.barrier()) if world > 1 else None)
     M = len(sc["pts"]); n_pts = [len(p) for p in sc["pts"]]
     edges = scene_graph(sc, cfg)
     param, cost = PARAM[cfg["param"]], COST[cfg["cost"]]
@@ -454,6 +467,8 @@ def run_ours(args, cfg):
         run_rounds(solo, args.steps, "dev", torch.cuda.ExternalStream(solo.stream(), device=dev))
         sha_1gpu = pose_sha(solo.get_poses())
         solo.close()
+    if world > 1:
+        dist.barrier()    # the other ranks wait for rank 0's replay before anybody tears its communicator down
     if rank == 0:
         peak, peak_src = hbm_peak()
         K = args.steps
