@@ -38,7 +38,9 @@ typedef struct {
   int32_t flags;        /* MVICP_FLAG_*                                                       */
   void*   stream;       /* cudaStream_t to run on (NULL: the context creates its own)         */
 } mvicp_config;
-enum { MVICP_FLAG_NO_ADJ = 8,     /* NN search: do not use the per-leaf neighbour lists (csrc/adjacency.h) that let a seeded query inside its
+enum { MVICP_FLAG_STEP_LOOP = 32, /* NN search: round 1's single loop of uniform steps instead of the while-while loop (csrc/knn.cuh
+                                      nn_drain); same matches, for A/B measurements */
+       MVICP_FLAG_NO_ADJ = 8,     /* NN search: do not use the per-leaf neighbour lists (csrc/adjacency.h) that let a seeded query inside its
                                       start leaf's reach skip the tree walk; same matches, for A/B measurements */
        MVICP_FLAG_HOST_BUILD = 4,  /* build the per-frame search trees on the host (csrc/tree_build.h) instead of on the device
                                       (csrc/tree_gpu.cuh); same matches, for A/B measurements */

@@ -19,6 +19,7 @@ FLAG_NCCL_ONLY = 2
 FLAG_HOST_BUILD = 4
 FLAG_NO_ADJ = 8
 FLAG_NO_OBB = 16
+FLAG_STEP_LOOP = 32
 
 
 def _p(a, t=C.c_double):

@@ -30,7 +30,7 @@ __device__ __forceinline__ float obb_lb32(const ObbNode* __restrict__ nodes, int
 }
 
 // nn_search of knn.cuh with the oriented lower bound (the split-plane pre-filter and the stale-seed rule are unchanged)
-template <bool F32>
+template <bool F32, bool WW>
 __device__ __forceinline__ void nn_search_obb(const FrameDev& fd, const ObbNode* __restrict__ ob, NNQuery& s, int start_leaf) {
   const int L = fd.n_leaf_pad;
   int leaf_node = -1;
@@ -67,31 +67,10 @@ __device__ __forceinline__ void nn_search_obb(const FrameDev& fd, const ObbNode*
     const float lb = obb_lb32(ob, sib, s);
     if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
   }
-  int node = -1, sub = 0;
-  while (true) {
-    if (node < 0) {
-      if (sp == 0) break;
-      --sp;
-      if (stk_lb[sp] > s.bound32) continue;
-      node = stk_n[sp]; sub = 0;
-    }
-    if (node >= L) {
-      nn_leaf_step<F32, NNQuery>(fd, node - L, sub, s);
-      if (++sub == LEAF / 2) node = -1;
-    } else {
-      const int c0 = 2 * node;
-      const float l0 = obb_lb32(ob, c0, s), l1 = obb_lb32(ob, c0 + 1, s);
-      const bool first0 = l0 <= l1;
-      const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
-      if (ln <= s.bound32) {
-        if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
-        node = first0 ? c0 : c0 + 1; sub = 0;
-      } else node = -1;
-    }
-  }
+  nn_drain<F32, WW, NNQuery>(fd, s, stk_n, stk_lb, sp, [&](int nd) { return obb_lb32(ob, nd, s); });
 }
 
-template <bool F32>
+template <bool F32, bool WW>
 __global__ void __launch_bounds__(KNN_TILE)
 knn_far_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
                const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
@@ -127,7 +106,7 @@ knn_far_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
     const int si = sd >= 0 ? sd : ~sd;
     if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
   }
-  nn_search_obb<F32>(fd, ob, nq, start_leaf);
+  nn_search_obb<F32, WW>(fd, ob, nq, start_leaf);
   const double best = nq.best; const int bi = nq.bi;
   const bool inlier = __dsqrt_rn(best) < thresh;
   corr[e.off + orig] = inlier ? bi : ~bi;

@@ -122,7 +122,64 @@ __device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int s
 // points of a leaf (a leaf takes LEAF/2 steps) -- so that the lanes of a warp, which sit at different nodes, still
 // execute the same instructions; only the trip count differs between lanes.
 constexpr int NN_STACK = 64;   // >= 2 * depth: flagged siblings + far children of one descent
-template <bool F32, class Q>
+// The rest of the search after the first root-to-leaf path: the stacked sibling subtrees, depth-first, nearest child first.
+// WW = false: every trip of ONE loop does one uniform step -- "test the two child boxes of the current node" or "test two points of
+//             the current leaf" -- whichever the lane needs (round 1's schedule);
+// WW = true:  "while-while" (Aila & Laine): an inner loop runs node steps only until the lane holds the next leaf that can matter,
+//             then all such lanes scan their leaves together -- a warp executes one kind of step at a time.
+// lb_of(node) is the fp32 lower bound of a node's box (axis-aligned in knn.cuh, hybrid oriented in far.cuh).
+template <bool F32, bool WW, class Q, class LBF>
+__device__ __forceinline__ void nn_drain(const FrameDev& fd, Q& s, int* stk_n, float* stk_lb, int sp, LBF lb_of) {
+  const int L = fd.n_leaf_pad;
+  if (WW) {
+    while (true) {
+      int leaf = -1;
+      while (sp > 0) {
+        --sp;
+        if (stk_lb[sp] > s.bound32) continue;
+        int node = stk_n[sp];
+        while (node < L) {   // descend: nearer child first, the other one onto the stack
+          const int c0 = 2 * node;
+          const float l0 = lb_of(c0), l1 = lb_of(c0 + 1);
+          const bool first0 = l0 <= l1;
+          const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
+          if (ln > s.bound32) { node = -1; break; }
+          if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+          node = first0 ? c0 : c0 + 1;
+        }
+        if (node >= L) { leaf = node - L; break; }
+      }
+      if (leaf < 0) break;
+#pragma unroll
+      for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, leaf, sub, s);
+    }
+  } else {
+    int node = -1, sub = 0;
+    while (true) {
+      if (node < 0) {
+        if (sp == 0) break;
+        --sp;
+        if (stk_lb[sp] > s.bound32) continue;
+        node = stk_n[sp]; sub = 0;
+      }
+      if (node >= L) {
+        nn_leaf_step<F32, Q>(fd, node - L, sub, s);
+        if (++sub == LEAF / 2) node = -1;
+      } else {
+        const int c0 = 2 * node;
+        const float l0 = lb_of(c0), l1 = lb_of(c0 + 1);
+        const bool first0 = l0 <= l1;
+        const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
+        if (ln <= s.bound32) {
+          if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+          node = first0 ? c0 : c0 + 1; sub = 0;
+        } else node = -1;
+      }
+    }
+  }
+}
+
+template <bool F32, class Q, bool WW = false>
 __device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_leaf) {
   const int L = fd.n_leaf_pad;
   int leaf_node = -1;
@@ -187,28 +244,7 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_le
     const float lb = box_lb32(fd.boxes, sib, s);
     if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
   }
-  int node = -1, sub = 0;
-  while (true) {
-    if (node < 0) {
-      if (sp == 0) break;
-      --sp;
-      if (stk_lb[sp] > s.bound32) continue;
-      node = stk_n[sp]; sub = 0;
-    }
-    if (node >= L) {
-      nn_leaf_step<F32, Q>(fd, node - L, sub, s);
-      if (++sub == LEAF / 2) node = -1;
-    } else {
-      const int c0 = 2 * node;
-      const float l0 = box_lb32(fd.boxes, c0, s), l1 = box_lb32(fd.boxes, c0 + 1, s);
-      const bool first0 = l0 <= l1;
-      const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
-      if (ln <= s.bound32) {
-        if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
-        node = first0 ? c0 : c0 + 1; sub = 0;
-      } else node = -1;
-    }
-  }
+  nn_drain<F32, WW, Q>(fd, s, stk_n, stk_lb, sp, [&](int nd) { return box_lb32(fd.boxes, nd, s); });
 }
 
 __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, double qz, float absmax) {
@@ -222,7 +258,7 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
 
 // One thread per (edge, src point) query; src points are walked in the src frame's tree order so that the
 // lanes of a warp descend the dst tree together.
-template <bool F32>
+template <bool F32, bool WW>
 __global__ void __launch_bounds__(KNN_TILE)
 knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
            const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
@@ -258,7 +294,7 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
     const int si = sd >= 0 ? sd : ~sd;
     if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
   }
-  nn_search<F32, NNQuery>(fd, nq, start_leaf);
+  nn_search<F32, NNQuery, WW>(fd, nq, start_leaf);
   const double best = nq.best; const int bi = nq.bi;
   const bool inlier = __dsqrt_rn(best) < thresh;
   corr[e.off + orig] = inlier ? bi : ~bi;

@@ -510,10 +510,16 @@ static int layout_work(mvicp_ctx* c) {
     if (ed.owned) owned_slots += ed.n_src;
   }
   c->total_slots = off;
-  // LM streaming tile: long enough to amortise the 28-value block reduction, short enough to fill 148 SMs
+  // LM streaming tile: long enough to amortise the 28-value block reduction, short enough to fill 148 SMs.  Its length fixes how
+  // an edge's sum is associated (per-tile partials, added in tile order), so it must not depend on how many ranks share the
+  // work: it is chosen from ALL active slots, and a sharded run's poses stay bit-identical to the single-GPU run's
+  // (bench.py checks that in every multi-GPU run; round 1 chose it from the rank's own share and was not).
+  int64_t active_slots = 0;
+  for (int e = 0; e < E; ++e) if (c->edge_owner[e] >= 0) active_slots += c->h_edges[e].n_src;
   int tl = 8192;
-  while (tl > 1024 && owned_slots / tl < 4 * 148) tl >>= 1;
+  while (tl > 1024 && active_slots / tl < 8 * 148) tl >>= 1;
   c->eval_tile_len = tl;
+  (void)owned_slots;
   std::vector<Tile> kt, et; std::vector<int32_t> etb(E + 1, 0);
   for (int e = 0; e < E; ++e) {
     const EdgeDev& ed = c->h_edges[e];
@@ -625,15 +631,14 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
     if (!seed || c->last_lm_iters == (1 << 20)) c->seeded_rounds = 0;
     const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1);
     if (seed) ++c->seeded_rounds;
-    if (far) {
-      knn_far_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
-          c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
-          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh, c->d_obb.as<ObbDev>());
-    } else {
-      knn_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(
-          c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(),
-          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh);
-    }
+    const bool ww = !(c->flags & MVICP_FLAG_STEP_LOOP);
+#define MV_KNN_ARGS c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(), \
+                    c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh
+    if (far && ww) knn_far_kernel<F32, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
+    else if (far) knn_far_kernel<F32, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
+    else if (ww) knn_kernel<F32, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS);
+    else knn_kernel<F32, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS);
+#undef MV_KNN_ARGS
   }
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);

@@ -5,7 +5,7 @@ import pytest
 
 from helpers import oracle_correspond, scene
 from mv_lm_icp_b200 import Engine, synth
-from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED
+from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED, FLAG_STEP_LOOP
 
 pytestmark = pytest.mark.gpu
 
@@ -46,7 +46,8 @@ def test_synthetic_bit_exact(oracle, n_views, n_points, cfg):
 
 
 SCHEDULES = (FLAG_NO_SEED, FLAG_NO_OBB, FLAG_NO_OBB | FLAG_NO_SEED, FLAG_HOST_BUILD, FLAG_HOST_BUILD | FLAG_NO_SEED, FLAG_HOST_BUILD | FLAG_NO_OBB,
-             FLAG_NO_ADJ, FLAG_NO_ADJ | FLAG_HOST_BUILD, FLAG_NO_ADJ | FLAG_NO_OBB | FLAG_NO_SEED)
+             FLAG_NO_ADJ, FLAG_NO_ADJ | FLAG_HOST_BUILD, FLAG_NO_ADJ | FLAG_NO_OBB | FLAG_NO_SEED,
+             FLAG_STEP_LOOP, FLAG_STEP_LOOP | FLAG_NO_SEED, FLAG_STEP_LOOP | FLAG_NO_ADJ | FLAG_NO_OBB)
 
 
 def test_seed_and_schedule_do_not_change_results(oracle, extra_flags=()):

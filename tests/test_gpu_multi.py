@@ -19,26 +19,36 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _run(rank, world, port, out_dir, flags):
+def _scene_file(out_dir, n_views, n_points, cfg):
+    """The parent generates the scene once; the spawned ranks load it."""
+    path = os.path.join(out_dir, f"scene_{n_views}x{n_points}.npz")
+    if not os.path.exists(path):
+        sc = scene(n_views, n_points, cfg)
+        np.savez(path, init=sc["poses_init"], **{f"p{i}": p for i, p in enumerate(sc["pts"])}, **{f"n{i}": p for i, p in enumerate(sc["nor"])})
+    z = np.load(path)
+    return {"pts": [z[f"p{i}"] for i in range(n_views)], "nor": [z[f"n{i}"] for i in range(n_views)], "poses_init": z["init"]}
+
+
+def _run(rank, world, port, out_dir, flags, n_views=6, n_points=20011, rounds=3):
     import torch.distributed as dist
     import mv_lm_icp_b200 as mv
     from mv_lm_icp_b200.dist import broadcast_unique_id
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    sc = scene(6, 20011, 22)
-    edges = synth.ring_edges(6, 2)
+    sc = _scene_file(out_dir, n_views, n_points, 22)
+    edges = synth.ring_edges(n_views, 2)
     eng = mv.Engine(device=rank, flags=flags)
     eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges)
     eng.comm_init(broadcast_unique_id(mv.nccl_unique_id, rank, device="cuda"), rank, world)
     eng.set_poses(sc["poses_init"])
     out = []
-    for _ in range(3):
+    for _ in range(rounds):
         s = eng.icp_round(0.05, mv.PARAM_SE3, mv.COST_P2PLANE, True)
         out.append((eng.get_poses(), s["num_iterations"]))
     # ownership: get_nn succeeds exactly on the edges dist.edge_owners gives this rank
     from mv_lm_icp_b200.dist import edge_owners
-    own = edge_owners(edges, [len(p) for p in sc["pts"]], world, [1] + [0] * 5)
+    own = edge_owners(edges, [len(p) for p in sc["pts"]], world, [1] + [0] * (n_views - 1))
     for e in range(len(edges)):
         try:
             eng.get_nn(e); mine = True
@@ -52,18 +62,21 @@ def _run(rank, world, port, out_dir, flags):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("flags", [0, 2], ids=["peer-memory", "nccl-only"])
-def test_two_gpus_bit_identical_to_one(tmp_path, flags):
+@pytest.mark.parametrize("flags,n_points,rounds", [(0, 20011, 3), (2, 20011, 3), (0, 300_000, 2)], ids=["peer-memory", "nccl-only", "peer-memory-300k"])
+def test_two_gpus_bit_identical_to_one(tmp_path, flags, n_points, rounds):
+    """300k points per view: enough slots that the LM streaming tile is longer than its minimum -- its length fixes how an edge's
+    sum is associated and must not depend on the number of ranks (round 1 derived it from the rank's own share: poses of a
+    sharded config-3 run differed from the single-GPU run's in the last bits, which the small case cannot see)."""
     import mv_lm_icp_b200 as mv
-    sc = scene(6, 20011, 22)
+    sc = _scene_file(str(tmp_path), 6, n_points, 22)
     edges = synth.ring_edges(6, 2)
     eng = mv.Engine(); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
     ref = []
-    for _ in range(3):
+    for _ in range(rounds):
         s = eng.icp_round(0.05, mv.PARAM_SE3, mv.COST_P2PLANE, True)
         ref.append((eng.get_poses(), s["num_iterations"]))
     eng.close()
-    mp.spawn(_run, args=(2, _free_port(), str(tmp_path), flags), nprocs=2, join=True)
+    mp.spawn(_run, args=(2, _free_port(), str(tmp_path), flags, 6, n_points, rounds), nprocs=2, join=True)
     for r in range(2):
         P = np.load(tmp_path / f"poses_{r}.npy"); it = np.load(tmp_path / f"iters_{r}.npy")
         assert it.tolist() == [x[1] for x in ref]

@@ -141,7 +141,7 @@ def test_headless_driver_on_the_emulated_engine(emu, tmp_path):
         assert len(m) == 4 and all(float(a) < 1e-8 and float(b) < 1e-4 for a, b in m[1:]) and (extra or float(m[0][0]) < 1e-12)
 
 
-@pytest.mark.parametrize("xflags", [8, 16, 25], ids=["no-adjacency", "no-obb", "no-adj-no-obb-no-seed"])
+@pytest.mark.parametrize("xflags", [8, 16, 25, 32], ids=["no-adjacency", "no-obb", "no-adj-no-obb-no-seed", "step-loop"])
 def test_schedules_are_bit_identical(emu, oracle, golden_dir, xflags):
     """Default: far rounds (no seeds yet / first seeded round) test the internal nodes against hybrid oriented boxes (csrc/far.cuh).
     MVICP_FLAG_NO_OBB: axis-aligned boxes only.  Same matches, same distances, same poses -- over ICP rounds that go from far to
