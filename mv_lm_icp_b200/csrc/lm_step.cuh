@@ -48,6 +48,7 @@ struct LmWork {
   double *H, *g, *Hc, *gc, *scale, *diag, *Lg, *rhs, *step;
   double* poses16;
   int32_t l_in_smem;
+  long long* prof;           // development aid (MVICP_STEP_PROFILE=1): clock64() stamps of the last solving launch, else null
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -145,7 +146,7 @@ __device__ __forceinline__ void chol_factor_diag(double* L, const int32_t* rb, i
 }
 
 __device__ bool chol_solve(double* L, const int32_t* __restrict__ rowbase, int n, double* scratch, double* dinv, double* y,
-                           const int32_t* __restrict__ rlast, const int32_t* __restrict__ rfirst) {
+                           const int32_t* __restrict__ rlast, const int32_t* __restrict__ rfirst, long long* prof = nullptr) {
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
   int32_t* s_rfirst = reinterpret_cast<int32_t*>(scratch);
   int32_t* s_rlast = s_rfirst + n;
@@ -158,8 +159,10 @@ __device__ bool chol_solve(double* L, const int32_t* __restrict__ rowbase, int n
   const int NB = n / 6;
   if (wid == 0) chol_factor_diag(L, rb, 0, dinv, s_ok, lane);
   __syncthreads();
+  long long t_panel = 0, t_ahead = 0, t_bar = 0;
   for (int J = 0; J < NB; ++J) {
     if (!*s_ok) return false;                     // uniform: written before the last barrier
+    const long long c0 = prof ? clock64() : 0;
     const int j0 = 6 * J;
     const int rl = s_rlast[j0 + 5];
     const int nrows = rl - (j0 + 5) + 1;          // rows j0+6..rl and the rhs row
@@ -179,7 +182,9 @@ __device__ bool chol_solve(double* L, const int32_t* __restrict__ rowbase, int n
 #pragma unroll
       for (int k = 0; k < 6; ++k) row[k] = v[k];
     }
+    const long long c1 = prof ? clock64() : 0;
     __syncthreads();
+    const long long c2 = prof ? clock64() : 0;
     // trailing update: A[r][c] -= sum_k L[r][j0+k] L[c][j0+k] for j0+5 < c <= min(r, rl)
     const bool next = J + 1 < NB;
     if (wid == 0 && next) {                       // look-ahead: the next diagonal block first, then its factor
@@ -216,8 +221,11 @@ __device__ bool chol_solve(double* L, const int32_t* __restrict__ rowbase, int n
         }
       }
     }
+    const long long c3 = prof ? clock64() : 0;
     __syncthreads();
+    if (prof) { const long long c4 = clock64(); t_panel += c1 - c0; t_ahead += c3 - c2; t_bar += (c2 - c1) + (c4 - c3); }
   }
+  if (prof && tid == 0) { prof[8] = t_panel; prof[9] = t_ahead; prof[10] = t_bar; }
   if (!*s_ok) return false;
   for (int i = tid; i < n; i += T) y[i] = L[rb[n] + i];   // forward-substituted rhs
   __syncthreads();
@@ -262,6 +270,9 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   __syncthreads();
   LmState* S = &s_state;
   const int n = S->n, M = S->M, E = S->E, param = S->param;
+  long long* prof = w.prof;
+#define MV_STAMP(i) do { if (prof && tid == 0) prof[i] = clock64(); } while (0)
+  MV_STAMP(0);
   if (w.peer_flags) {   // wait until every rank's edge kernel has delivered this iteration's pair matrices
     if (tid < w.world) {
       const long long t0 = clock64();
@@ -299,6 +310,7 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   for (int e = tid; e < E; e += T) eval_cost += w.eout[(size_t)EOUT * e + 156];
   eval_cost = block_sum(eval_cost, red);
 
+  MV_STAMP(1);
   // ================= 2. accept / reject / terminate =================================================
   bool take = false;    // the evaluation point becomes the accepted point
   if (tid == 0) {
@@ -367,6 +379,7 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     __syncthreads();
   }
 
+  MV_STAMP(2);
   // ================= 3. next trust-region step ======================================================
   while (!S->done) {
     __syncthreads();
@@ -396,7 +409,9 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
     }
     { const int rbn = w.rowbase[n]; for (int j = tid; j < n; j += T) L[rbn + j] = w.scale[j] * w.g[j]; }
     __syncthreads();
-    bool ok = chol_solve(L, w.rowbase, n, colj, dg, w.rhs, w.rlast, w.rfirst);
+    MV_STAMP(3);
+    bool ok = chol_solve(L, w.rowbase, n, colj, dg, w.rhs, w.rlast, w.rfirst, prof);
+    MV_STAMP(4);
     double bad = 0.0;
     if (ok) for (int j = tid; j < n; j += T) if (!isfinite(w.rhs[j])) bad = 1.0;
     bad = block_sum(bad, red);
@@ -445,6 +460,7 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
       if (w.G_eval && param != PARAM_AA) frame_general(param, xp, &w.G_eval[f]);
     }
     sn = block_sum(sn, red);
+    MV_STAMP(5);
     if (tid == 0) S->step_norm = sqrt(sn);
     __syncthreads();
     break;
@@ -461,7 +477,10 @@ __global__ void __launch_bounds__(STEP_THREADS) lm_step_kernel(LmWork w) {
   for (int i = tid; i < (int)(sizeof(LmState) / sizeof(int32_t)); i += T)
     reinterpret_cast<int32_t*>(w.S)[i] = reinterpret_cast<const int32_t*>(&s_state)[i];
   __syncthreads();
+  MV_STAMP(6);
   if (tid == 0) { __threadfence(); w.host_flag[w.seq & 7] = (w.seq << 1) | (S->done ? 1 : 0); __threadfence_system(); }
+  MV_STAMP(7);
+#undef MV_STAMP
 }
 
 }  // namespace mv

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -84,6 +85,7 @@ struct mvicp_ctx {
   DevBuf d_obb;                // ObbDev per frame (unless MVICP_FLAG_NO_OBB)
   int seeded_rounds = 0;       // consecutive mvicp_correspond calls that started from the previous call's matches
   DevBuf d_single;             // result slot of mvicp_closest_point
+  DevBuf d_prof;               // lm_step_kernel's clock stamps (MVICP_STEP_PROFILE=1)
   DevBuf d_tile_count, d_tile_off, d_edge_off, d_recs;   // mvicp_get_all_edges
   bool obb_ready = false;
   int last_lm_iters = 1 << 20; // LM iterations of the previous mvicp_optimize: large = the clouds are still far apart
@@ -357,7 +359,7 @@ void mvicp_destroy(mvicp_ctx* c) {
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
-                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_rowbase, &c->d_gen, &c->d_obb, &c->d_single, &c->d_tile_count, &c->d_tile_off, &c->d_edge_off, &c->d_recs};
+                    &c->d_gc_side, &c->d_posegather, &c->d_rlast, &c->d_rfirst, &c->d_rowbase, &c->d_gen, &c->d_obb, &c->d_single, &c->d_prof, &c->d_tile_count, &c->d_tile_off, &c->d_edge_off, &c->d_recs};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->eval_ev) cudaEventDestroy(ev);
@@ -928,6 +930,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   LmWork w{};
   w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.eout = c->d_eout.as<double>();
   w.host_flag = c->d_flag;
+  if (std::getenv("MVICP_STEP_PROFILE")) { RET(c->d_prof.reserve(sizeof(long long) * 16)); w.prof = c->d_prof.as<long long>(); }
   const bool general = c->nonrigid && param != PARAM_AA;
   if (general) { RET(c->d_gen.reserve(sizeof(FrameGen) * M)); RET(c->d_partial.reserve(sizeof(double) * GBLK * std::max<size_t>(1, c->n_eval_tiles))); }
   w.G_eval = general ? c->d_gen.as<FrameGen>() : nullptr;
@@ -1336,6 +1339,13 @@ int mvicp_get_stats(mvicp_ctx* c, mvicp_stats* out) {
     c->stats.correspondences = s;
   }
   *out = c->stats;
+  return MVICP_OK;
+}
+// development aid: the 16 clock64() stamps lm_step_kernel left when MVICP_STEP_PROFILE=1 (0..7 phase boundaries, 8..10 Cholesky parts)
+int mvicp_debug_step_profile(mvicp_ctx* c, long long* out16) {
+  if (!c || !out16 || !c->d_prof.p) return fail(MVICP_ERR_STATE, "mvicp_debug_step_profile: run with MVICP_STEP_PROFILE=1");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(out16, c->d_prof.p, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
   return MVICP_OK;
 }
 int mvicp_get_stream(mvicp_ctx* c, void** stream) { if (!c || !stream) return fail(MVICP_ERR_INVALID, "bad arguments"); *stream = (void*)c->stream; return MVICP_OK; }
