@@ -19,6 +19,7 @@ using std::min; using std::isfinite;
 #define __device__
 #define __forceinline__ inline
 static double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+static long long clock64() { return 0; }
 #define __restrict__
 struct Dim { int x; };
 static Dim blockDim{512};
