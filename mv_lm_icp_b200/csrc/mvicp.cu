@@ -149,6 +149,20 @@ static void assign_edge_owners(mvicp_ctx* c) {
 
 extern "C" { static int refresh_after_fixed_change(mvicp_ctx* c); }
 
+// Does some pose's rotation part yield a quaternion that is not unit (to 1e-9)?  Then the reference's quaternion / SE3 functors run
+// on non-unit quaternions (no normalisation anywhere, so3.hpp:666-668) and the LM step takes the general frame model.  True for
+// non-rigid input (the Bunny_RealData sample poses), and it can BECOME true: every solve writes q -> matrix back without
+// normalising (eigenQuaternionToIso / sophusToIso, icp-ceres.cpp:117-134), so the quaternion parameterisation drifts.
+static bool poses_nonrigid(const double* poses16, int M) {
+  for (int f = 0; f < M; ++f) {
+    Rt a; pose16_to_Rt(poses16 + 16 * f, &a);
+    double q[4]; quat_of_matrix(a.R, q);
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (!(std::fabs(n2 - 1.0) <= 1e-9)) return true;
+  }
+  return false;
+}
+
 // worker threads for the one-time host work: the CPUs this process may use (affinity mask, cgroup v2 quota), not the machine's
 static unsigned host_workers() {
   unsigned n = std::max(1u, std::thread::hardware_concurrency());
@@ -478,13 +492,7 @@ int mvicp_set_poses(mvicp_ctx* c, const double* poses16, const uint8_t* fixed) {
   // Non-rigid "isometries" (e.g. the reference's Bunny_RealData sample poses) give non-unit quaternions, on which the
   // reference's quaternion / SE3 functors keep running (no normalisation, so3.hpp:666-668): remember it, the LM step
   // then uses the general frame model.  Sticky until the next upload: a fixed frame keeps its non-unit quaternion.
-  c->nonrigid = false;
-  for (int f = 0; f < c->M; ++f) {
-    Rt a; pose16_to_Rt(poses16 + 16 * f, &a);
-    double q[4]; quat_of_matrix(a.R, q);
-    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
-    if (!(std::fabs(n2 - 1.0) <= 1e-9)) c->nonrigid = true;
-  }
+  c->nonrigid = poses_nonrigid(poses16, c->M);
   return MVICP_OK;
 }
 
@@ -931,6 +939,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.eout = c->d_eout.as<double>();
   w.host_flag = c->d_flag;
   if (std::getenv("MVICP_STEP_PROFILE")) { RET(c->d_prof.reserve(sizeof(long long) * 16)); w.prof = c->d_prof.as<long long>(); }
+  c->nonrigid = poses_nonrigid(c->h_poses.data(), M);   // the mirror follows every solve and every mvicp_set_poses
   const bool general = c->nonrigid && param != PARAM_AA;
   if (general) { RET(c->d_gen.reserve(sizeof(FrameGen) * M)); RET(c->d_partial.reserve(sizeof(double) * GBLK * std::max<size_t>(1, c->n_eval_tiles))); }
   w.G_eval = general ? c->d_gen.as<FrameGen>() : nullptr;

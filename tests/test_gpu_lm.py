@@ -233,3 +233,27 @@ def test_frame0_is_fixed_inside_the_optimiser():
         icp.engine.close()
     assert np.max(np.abs(out[0][0] - sc["poses_init"][0])) < 1e-14   # frame 0 only goes through the parameter round trip (icp-ceres.cpp:472-474)
     assert np.max(np.abs(out[0] - out[1])) < 1e-12
+
+
+def test_quaternion_parameterisation_drifts_off_the_unit_sphere(oracle):
+    """Every solve writes quaternion -> matrix back without normalising (icp-ceres.cpp:117-122) and the next one reads it with
+    Quaterniond(matrix): over many rounds with the Eigen-quaternion parameterisation the quaternions leave the unit sphere by more
+    than the 1e-9 the unit-quaternion LM path assumes.  The reference just keeps going on non-unit quaternions; the engine must
+    switch to its general frame model (found by the 20-round config-4 run, which stopped with MVICP_ERR_NONRIGID) and stay
+    within the contract of the oracle, which restates the non-unit arithmetic."""
+    sc = scene(4, 3000, 7)
+    edges = synth.ring_edges(4, 2)
+    eng = Engine(); eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
+    poses = sc["poses_init"].copy()
+    worst = 0.0
+    for rnd in range(30):
+        s = eng.icp_round(0.05, PARAM_QUAT, COST_MIXED, True)      # poses stay on the device between rounds, as in bench.py
+        ref = oracle_correspond(oracle, sc["pts"], poses, edges)
+        corr = [((r["first"], r["second"]) if r else (np.zeros(0, np.int32), np.zeros(0, np.int32))) for r in ref]
+        w = [np.float32(r["weight"]) if r else np.float32(0) for r in ref]
+        poses, sref, _ = oracle.optimize(sc["pts"], sc["nor"], poses, edges, corr, w, param=PARAM_QUAT, cost=COST_MIXED, robust=True, threads=8)
+        P = eng.get_poses()
+        worst = max(worst, pose_rel_err(P, poses))
+        eng.set_poses(poses)      # both sides continue from the oracle's poses: identical inputs every round
+    assert worst <= POSE_TOL, worst
+    eng.close()
