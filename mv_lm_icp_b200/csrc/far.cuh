@@ -1,13 +1,13 @@
-// far.cuh -- EXPERIMENTAL (MVICP_FLAG_OBB_FAR): the NN search of knn.cuh with HYBRID ORIENTED node boxes, for the rounds in
-// which the clouds are still far apart.  Same results as knn_kernel, bit for bit.
+// far.cuh -- the NN search of knn.cuh with HYBRID ORIENTED node boxes, for the rounds in which the clouds are still far
+// apart (a round without seeds and the first round that has them).  Same results as knn_kernel, bit for bit.
 //
 // A depth scan is a tilted, locally flat sheet: its axis-aligned boxes are as thick as the tilt makes them, and a query
 // that is still millimetres off the surface has to open every box within sqrt(height x thickness) of its foot point.  Nodes
 // of up to 64 points therefore get the box of their principal axes when that is clearly smaller (volume ratio < 0.5), all
-// others keep the coordinate axes (KD siblings stay disjoint near the root).  Measured on a B200 when it replaced the
-// AABBs everywhere (profiles/README.md, history): round 0 of config 3 13.3 -> 9.6 ms, converged rounds 1.40 -> 1.69 ms
-// (64-byte nodes) -- hence a separate node array used only while the previous LM solve still needed several iterations,
-// the converged rounds keeping the 32-byte AABB search (or the graph walk).
+// others keep the coordinate axes (KD siblings stay disjoint near the root).  Measured on a B200 (profiles/r2, config 3):
+// round 0 11.1 -> 9.0 ms, round 1 6.6 -> 5.9 ms; from the second seeded round on the 32-byte AABB nodes of knn.cuh win
+// (64-byte nodes cost more than the tighter boxes save once the seeds are good), hence a second node array and the switch
+// in mvicp_correspond.  MVICP_FLAG_NO_OBB builds no such array: every round then runs knn_kernel.
 #pragma once
 #include "knn.cuh"
 
@@ -40,6 +40,7 @@ __device__ __forceinline__ void nn_search_obb(const FrameDev& fd, const ObbNode*
     for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, NNQuery>(fd, start_leaf, sub, s);
     const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
     const float4 u = __ldg(b), v = __ldg(b + 1);
+    if (nn_adj_fast<F32, NNQuery>(fd, s, start_leaf, u, v)) return;      // a seed that is still good: the neighbour lists of knn.cuh
     const float ex = u.w - u.x, ey = v.x - u.y, ez = v.y - u.z;
     if (s.bound32 > 16.0f * fmaf(ez, ez, fmaf(ey, ey, ex * ex))) start_leaf = -1;
   }

@@ -179,6 +179,33 @@ __device__ __forceinline__ void nn_drain(const FrameDev& fd, Q& s, int* stk_n, f
   }
 }
 
+// Inside the start leaf's reach (adjacency.h) the answer lies in this leaf -- already scanned by the caller, (u, v) its box -- or
+// in one of its listed neighbours: test their boxes, scan the ones that can still hold a closer point; no walk up the ancestors,
+// no descents.  Returns false, having done nothing, when the query is not inside the reach.
+template <bool F32, class Q>
+__device__ __forceinline__ bool nn_adj_fast(const FrameDev& fd, Q& s, int start_leaf, const float4 u, const float4 v) {
+  if (!fd.adj) return false;
+  const int L = fd.n_leaf_pad;
+  const int32_t* ap = fd.adj + (size_t)ADJ_SLOTS * start_leaf;
+  const int2 hd = __ldg(reinterpret_cast<const int2*>(ap));
+  const float ex0 = fmaxf(fmaxf(u.x - s.fx, s.fx - u.w), 0.f), ey0 = fmaxf(fmaxf(u.y - s.fy, s.fy - v.x), 0.f), ez0 = fmaxf(fmaxf(u.z - s.fz, s.fz - v.y), 0.f);
+  const float e2 = fmaf(ez0, ez0, fmaf(ey0, ey0, ex0 * ex0));
+  // e + r <= R_S, every operation rounded up; the error of e (query and box in fp32) is inside the allowance that bound32 carries
+  if (!(__fadd_ru(sqrt_upper(e2), sqrt_upper(s.bound32)) <= __int_as_float(hd.x))) return false;
+  unsigned todo = 0u;
+  for (int i = 0; i < hd.y; ++i) {
+    const int t = __ldg(ap + 2 + i);
+    if (box_lb32(fd.boxes, L + t, s) <= s.bound32) todo |= 1u << i;
+  }
+  while (todo) {
+    const int i = __ffs(todo) - 1; todo &= todo - 1u;
+    const int t = __ldg(ap + 2 + i);
+#pragma unroll
+    for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, t, sub, s);
+  }
+  return true;
+}
+
 template <bool F32, class Q, bool WW = false>
 __device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_leaf) {
   const int L = fd.n_leaf_pad;
@@ -189,29 +216,7 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_le
     for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, start_leaf, sub, s);
     const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
     const float4 u = __ldg(b), v = __ldg(b + 1);
-    if (fd.adj) {
-      // Inside the start leaf's reach (adjacency.h) the answer lies in this leaf or in one of its listed neighbours: test their
-      // boxes, scan the ones that can still hold a closer point -- no walk up the ancestors, no descents.
-      const int32_t* ap = fd.adj + (size_t)ADJ_SLOTS * start_leaf;
-      const int2 hd = __ldg(reinterpret_cast<const int2*>(ap));
-      const float ex0 = fmaxf(fmaxf(u.x - s.fx, s.fx - u.w), 0.f), ey0 = fmaxf(fmaxf(u.y - s.fy, s.fy - v.x), 0.f), ez0 = fmaxf(fmaxf(u.z - s.fz, s.fz - v.y), 0.f);
-      const float e2 = fmaf(ez0, ez0, fmaf(ey0, ey0, ex0 * ex0));
-      // e + r <= R_S, every operation rounded up; the error of e (query and box in fp32) is inside the allowance that bound32 carries
-      if (__fadd_ru(sqrt_upper(e2), sqrt_upper(s.bound32)) <= __int_as_float(hd.x)) {
-        unsigned todo = 0u;
-        for (int i = 0; i < hd.y; ++i) {
-          const int t = __ldg(ap + 2 + i);
-          if (box_lb32(fd.boxes, L + t, s) <= s.bound32) todo |= 1u << i;
-        }
-        while (todo) {
-          const int i = __ffs(todo) - 1; todo &= todo - 1u;
-          const int t = __ldg(ap + 2 + i);
-#pragma unroll
-          for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, Q>(fd, t, sub, s);
-        }
-        return;
-      }
-    }
+    if (nn_adj_fast<F32, Q>(fd, s, start_leaf, u, v)) return;
     // a stale guess (the poses moved a lot since it was made) leaves a loose bound, and everything inside that ball
     // would be visited on the way up: if the guess is further than a few leaf sizes, descend greedily instead
     const float ex = u.w - u.x, ey = v.x - u.y, ez = v.y - u.z;                 // extents of the leaf

@@ -639,7 +639,9 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
     // 11.1 -> 9.0 ms, round 1 6.6 -> 5.9 ms; from the second seeded round on the 32-byte AABB nodes win (4.57 vs 4.96 ms).
     // Poses set from outside since the last solve count as a fresh start.
     if (!seed || c->last_lm_iters == (1 << 20)) c->seeded_rounds = 0;
-    const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1);
+    // A/B knob (flags bits 8-11 = n > 0): seeded rounds also count as far while the previous solve took >= n LM iterations
+    const int far_iters = (c->flags >> 8) & 15;
+    const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1 || (far_iters > 0 && c->last_lm_iters >= far_iters));
     if (seed) ++c->seeded_rounds;
     const bool ww = !(c->flags & MVICP_FLAG_STEP_LOOP);
 #define MV_KNN_ARGS c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(), \

@@ -77,6 +77,7 @@ def test_lm_pipeline_pairwise_and_general_path(emu, oracle, golden_dir):
         return
     T.test_pipeline_round_matches_oracle(oracle)
     T.test_frame0_is_fixed_inside_the_optimiser()
+    T.test_quaternion_parameterisation_drifts_off_the_unit_sphere(oracle)
     for name, param, cost in (("pointToPoint_CeresAngleAxis", 0, 0), ("pointToPoint_EigenQuaternion", 1, 0), ("pointToPoint_SophusSE3", 2, 0),
                               ("pointToPlane_CeresAngleAxis", 0, 1), ("pointToPlane_EigenQuaternion", 1, 1), ("pointToPlane_SophusSE3", 2, 1)):
         T.test_pairwise_known_answer(oracle, golden_dir, name, param, cost)
