@@ -38,8 +38,6 @@ typedef struct {
   int32_t flags;        /* MVICP_FLAG_*                                                       */
   void*   stream;       /* cudaStream_t to run on (NULL: the context creates its own)         */
 } mvicp_config;
-/* flags bits 8-11 (development A/B): n > 0 = seeded NN rounds keep searching the oriented boxes while the previous solve took >= n LM iterations */
-#define MVICP_FLAG_FAR_ITERS(n) (((n) & 15) << 8)
 enum { MVICP_FLAG_STEP_LOOP = 32, /* NN search: round 1's single loop of uniform steps instead of the while-while loop (csrc/knn.cuh
                                       nn_drain); same matches, for A/B measurements */
        MVICP_FLAG_NO_ADJ = 8,     /* NN search: do not use the per-leaf neighbour lists (csrc/adjacency.h) that let a seeded query inside its

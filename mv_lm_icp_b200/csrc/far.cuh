@@ -7,7 +7,8 @@
 // others keep the coordinate axes (KD siblings stay disjoint near the root).  Measured on a B200 (profiles/r2, config 3):
 // round 0 11.1 -> 9.0 ms, round 1 6.6 -> 5.9 ms; from the second seeded round on the 32-byte AABB nodes of knn.cuh win
 // (64-byte nodes cost more than the tighter boxes save once the seeds are good), hence a second node array and the switch
-// in mvicp_correspond.  MVICP_FLAG_NO_OBB builds no such array: every round then runs knn_kernel.
+// in mvicp_correspond.  MVICP_FLAG_NO_OBB builds no such array: every round then runs knn_kernel.  (Trying the per-leaf
+// neighbour lists of knn.cuh first, for the seeds that are still good, measured no gain here: 3.52 -> 3.65 ms in round 1.)
 #pragma once
 #include "knn.cuh"
 
@@ -40,7 +41,6 @@ __device__ __forceinline__ void nn_search_obb(const FrameDev& fd, const ObbNode*
     for (int sub = 0; sub < LEAF / 2; ++sub) nn_leaf_step<F32, NNQuery>(fd, start_leaf, sub, s);
     const float4* b = reinterpret_cast<const float4*>(fd.boxes + leaf_node);
     const float4 u = __ldg(b), v = __ldg(b + 1);
-    if (nn_adj_fast<F32, NNQuery>(fd, s, start_leaf, u, v)) return;      // a seed that is still good: the neighbour lists of knn.cuh
     const float ex = u.w - u.x, ey = v.x - u.y, ez = v.y - u.z;
     if (s.bound32 > 16.0f * fmaf(ez, ez, fmaf(ey, ey, ex * ex))) start_leaf = -1;
   }

@@ -367,113 +367,144 @@ lm_edge_kernel(const EdgeDev* __restrict__ edges, const int32_t* __restrict__ ed
 }
 
 
-// ---- general path: non-unit quaternions (non-rigid input poses) -------------------------------------------------------
+// ---- general path: non-unit quaternions (non-rigid input poses, or quaternion poses that drifted) ----------------------
 // Same contract as lm_eval_kernel, for the frame model of frame_general(): y = F v + t with F no rotation, Jacobian rows
-// through the per-frame matrices D_j, c_j (the relative-pose shortcut needs orthogonal F).  The 12x12 pair matrix is
-// accumulated directly, one block per launch to bound the register count (PASS 0: (s,s) + gradient + cost, 1: (s,k),
-// 2: (k,k)); three passes over the correspondences -- this path only runs on inputs that are not rigid transforms.
+// through the per-frame matrices D_j, c_j (the relative-pose shortcut needs orthogonal F), the 12x12 pair matrix accumulated
+// directly: 78 + 12 + 1 sums per correspondence.  That is too many fp64 accumulators for one thread, and splitting them over
+// passes (rounds 1-2: three) recomputes the Jacobian row in each -- 70 % of the arithmetic.  So TWO LANES share a
+// correspondence: the even lane owns the src frame's half of the row, the odd lane the dst frame's; they swap halves with one
+// shuffle per entry, and each accumulates its own diagonal block (21), half of the off-diagonal block (18), its half of the
+// gradient (6) -- 46 sums per lane, one pass, the row computed once.  Both lanes run the same instruction stream (role-selected
+// operands, no divergence).  The tangent is handled in the order (rotation, translation): D_j = 0 for translation directions
+// and c_j = 0 for rotation directions in both parameterisations (frame_general), which halves the row's cost; `rot0` (0:
+// quaternion, 3: SE3) maps that order back when the sums are written.
 constexpr int GBLK = 96;   // stride of a general partial: 78 (upper 12x12) | 12 | 1
+constexpr int GACC = 46;   // per lane: 21 own block | 18 half of the (s,k) block | 6 gradient | cost
 __device__ __forceinline__ int u12(int i, int j) { return i * 12 - (i * (i - 1)) / 2 + (j - i); }
 
-template <bool F32, bool NF32, int COST, int PASS>
-__device__ __forceinline__ void lm_eval_general_pass(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
+template <bool F32, bool NF32, int COST>
+__global__ void __launch_bounds__(EVAL_THREADS)
+lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
                        int tile_len, const int32_t* __restrict__ corr, const FrameGen* __restrict__ frame_gen,
-                       const float* __restrict__ weight, int robust, double* __restrict__ partial) {
+                       const float* __restrict__ weight, int robust, int rot0, double* __restrict__ partial, const int* __restrict__ done_flag) {
+  if (*done_flag) return;
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
-  __shared__ FrameGen gs, gk;
-  __shared__ double sred[EVAL_THREADS / 32][49];
+  __shared__ FrameGen g2[2];                                    // [0] src frame, [1] dst frame
+  __shared__ double sred[EVAL_THREADS / 32][2][GACC];
   {
     const double* a = reinterpret_cast<const double*>(frame_gen + e.src); const double* b = reinterpret_cast<const double*>(frame_gen + e.dst);
-    double* sa = reinterpret_cast<double*>(&gs); double* sb = reinterpret_cast<double*>(&gk);
+    double* sa = reinterpret_cast<double*>(&g2[0]); double* sb = reinterpret_cast<double*>(&g2[1]);
     for (int i = threadIdx.x; i < (int)(sizeof(FrameGen) / sizeof(double)); i += blockDim.x) { sa[i] = a[i]; sb[i] = b[i]; }
   }
   __syncthreads();
+  const int role = threadIdx.x & 1;                              // 0: src half of the row, 1: dst half
+  const FrameGen& gs = g2[0]; const FrameGen& gk = g2[1]; const FrameGen& gm = g2[role];
+  const int tra0 = 3 - rot0;
+  const double sgn = role ? -1.0 : 1.0;
   const double a_w = (double)weight[t.edge];
   const double bb = a_w * a_w, cc = 1.0 / bb;
   const FrameDev fs = frames[e.src];
   const FrameDev fd = frames[e.dst];
-  constexpr int NACC = PASS == 0 ? 21 + 12 + 1 : (PASS == 1 ? 36 : 21);
-  double acc[NACC];
+  double acc[GACC];
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  for (int i = 0; i < GACC; ++i) acc[i] = 0.0;
   const int end = min(t.start + tile_len, e.n_src);
-  for (int k = t.start + threadIdx.x; k < end; k += EVAL_THREADS) {
-    const int c = __ldg(corr + e.off + k);
-    if (c < 0) continue;
-    double p[3], q[3], n[3] = {0, 0, 0}; int dummy;
-    Rec<F32>::load(fs.pts_o, k, p[0], p[1], p[2], dummy);
-    Rec<F32>::load(fd.pts_o, c, q[0], q[1], q[2], dummy);
-    if (COST != COST_P2P) Rec<NF32>::load(fd.nor_o, c, n[0], n[1], n[2], dummy);
+  for (int k0 = t.start; k0 < end; k0 += EVAL_THREADS / 2) {    // uniform trip count: the pair shuffles need every lane
+    const int k = k0 + (threadIdx.x >> 1);
+    const int c = k < end ? __ldg(corr + e.off + k) : -1;
+    const bool ok = c >= 0;
+    if (!__any_sync(0xffffffffu, ok)) continue;
+    double p[3] = {0, 0, 0}, q[3] = {0, 0, 0}, n[3] = {0, 0, 0}; int dummy;
+    if (ok) {
+      Rec<F32>::load(fs.pts_o, k, p[0], p[1], p[2], dummy);
+      Rec<F32>::load(fd.pts_o, c, q[0], q[1], q[2], dummy);
+      if (COST != COST_P2P) Rec<NF32>::load(fd.nor_o, c, n[0], n[1], n[2], dummy);
+    }
+    const double live = ok ? 1.0 : 0.0;                          // an empty slot adds exact zeros
     double ys[3], yk[3], n2[3], d[3];
     matvec(gs.F, p, ys); matvec(gk.F, q, yk); matvec(gk.F, n, n2);
+#pragma unroll
     for (int i = 0; i < 3; ++i) d[i] = (ys[i] + gs.t[i]) - (yk[i] + gk.t[i]);
-    // columns of the world-frame point Jacobians: dys[j] = D^s_j p + c^s_j, dyk[j] = D^k_j q + c^k_j, dn[j] = D^k_j n
+    // this lane's half of the point Jacobians: rotation directions D_j v, translation directions c_j  (v = p | q)
+    const double v[3] = {role ? q[0] : p[0], role ? q[1] : p[1], role ? q[2] : p[2]};
+    const double dk[3] = {role ? d[0] : 0.0, role ? d[1] : 0.0, role ? d[2] : 0.0};      // the d . (D_j n) term exists on the dst side only
+    double a3[3][3], cn[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { matvec(gm.D[rot0 + j], v, a3[j]); if (COST != COST_P2P) matvec(gm.D[rot0 + j], n, cn[j]); }
+#pragma unroll
     for (int blk = 0; blk < 2; ++blk) {
       const bool plane = blk == 1;
       if (plane && COST == COST_P2P) continue;
       if (!plane && COST == COST_P2PLANE) continue;
       const int nr = plane ? 1 : 3;
-      double J[3][12], r[3];
-      for (int j = 0; j < 6; ++j) {
-        double a3[3], b3[3], c3[3];
-        matvec(gs.D[j], p, a3); matvec(gk.D[j], q, b3);
-        for (int i = 0; i < 3; ++i) { a3[i] += gs.c[j][i]; b3[i] += gk.c[j][i]; }
-        if (plane) {
-          matvec(gk.D[j], n, c3);
-          J[0][j] = n2[0] * a3[0] + n2[1] * a3[1] + n2[2] * a3[2];
-          J[0][6 + j] = -(n2[0] * b3[0] + n2[1] * b3[1] + n2[2] * b3[2]) + (d[0] * c3[0] + d[1] * c3[1] + d[2] * c3[2]);
-        } else {
-          for (int i = 0; i < 3; ++i) { J[i][j] = a3[i]; J[i][6 + j] = -b3[i]; }
-        }
-      }
+      double r[3];
       if (plane) r[0] = d[0] * n2[0] + d[1] * n2[1] + d[2] * n2[2]; else { r[0] = d[0]; r[1] = d[1]; r[2] = d[2]; }
-      double s = 0; for (int i = 0; i < nr; ++i) s += r[i] * r[i];
+      double s = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) if (i < nr) s += r[i] * r[i];
       double w = 1.0, cst;
       if (robust) { const double arg = 1.0 + s * cc; w = rsqrt(arg); cst = bb * (arg * w - 1.0); } else cst = 0.5 * s;
-      for (int i = 0; i < nr; ++i) {
-        if (PASS == 0) {
-          int idx = 0;
-          for (int a = 0; a < 6; ++a) { const double wa = w * J[i][a]; for (int b = a; b < 6; ++b) acc[idx++] += wa * J[i][b]; }
-          for (int a = 0; a < 12; ++a) acc[21 + a] += w * J[i][a] * r[i];
-        } else if (PASS == 1) {
-          for (int a = 0; a < 6; ++a) { const double wa = w * J[i][a]; for (int b = 0; b < 6; ++b) acc[6 * a + b] += wa * J[i][6 + b]; }
-        } else {
-          int idx = 0;
-          for (int a = 0; a < 6; ++a) { const double wa = w * J[i][6 + a]; for (int b = a; b < 6; ++b) acc[idx++] += wa * J[i][6 + b]; }
+      w *= live; cst *= live;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i >= nr) continue;
+        double Jm[6], Jo[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double* cj = gm.c[tra0 + j];
+          if (plane) {
+            Jm[j] = sgn * (n2[0] * a3[j][0] + n2[1] * a3[j][1] + n2[2] * a3[j][2]) + (dk[0] * cn[j][0] + dk[1] * cn[j][1] + dk[2] * cn[j][2]);
+            Jm[3 + j] = sgn * (n2[0] * cj[0] + n2[1] * cj[1] + n2[2] * cj[2]);
+          } else { Jm[j] = sgn * a3[j][i]; Jm[3 + j] = sgn * cj[i]; }
         }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Jo[j] = __shfl_xor_sync(0xffffffffu, Jm[j], 1);
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { const double wa = w * Jm[a];
+#pragma unroll
+          for (int b = a; b < 6; ++b) acc[idx++] += wa * Jm[b]; }
+        // (s,k) block: rows 0-2 of it on the even lane, rows 3-5 on the odd lane; X = src-side entries of those rows, Y = the dst side
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const double wx = w * (role ? Jo[3 + a] : Jm[a]);
+#pragma unroll
+          for (int b = 0; b < 6; ++b) acc[21 + 6 * a + b] += wx * (role ? Jm[b] : Jo[b]); }
+        const double wr = w * r[i];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[39 + a] += wr * Jm[a];
       }
-      if (PASS == 0) acc[33] += cst;
+      acc[45] += cst;
     }
   }
+  // sum over the lanes of equal role (xor 16, 8, 4, 2), then over the warps in order
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = 0; i < NACC; ++i) { const double v = warp_sum(acc[i]); if (lane == 0) sred[wid][i] = v; }
-  __syncthreads();
-  if (threadIdx.x < NACC) {
-    double v = 0.0;
-    for (int w = 0; w < EVAL_THREADS / 32; ++w) v += sred[w][threadIdx.x];
-    // scatter into the 12x12 upper-triangle layout
-    const int i = threadIdx.x; int dst;
-    if (PASS == 0) {
-      if (i < 21) { int a = 0, rem = i; while (rem >= 6 - a) { rem -= 6 - a; ++a; } dst = u12(a, a + rem); }
-      else if (i < 33) dst = 78 + (i - 21);
-      else dst = 90;
-    } else if (PASS == 1) dst = u12(i / 6, 6 + i % 6);
-    else { int a = 0, rem = i; while (rem >= 6 - a) { rem -= 6 - a; ++a; } dst = u12(6 + a, 6 + a + rem); }
-    partial[(size_t)blockIdx.x * GBLK + dst] = v;
+#pragma unroll
+  for (int i = 0; i < GACC; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane < 2) sred[wid][lane][i] = v;
   }
-}
-
-// the three passes in one launch: blockIdx.y = pass (each writes its own part of the tile's partial)
-template <bool F32, bool NF32, int COST>
-__global__ void __launch_bounds__(EVAL_THREADS)
-lm_eval_general_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const Tile* __restrict__ tiles,
-                       int tile_len, const int32_t* __restrict__ corr, const FrameGen* __restrict__ frame_gen,
-                       const float* __restrict__ weight, int robust, double* __restrict__ partial, const int* __restrict__ done_flag) {
-  if (*done_flag) return;
-  if (blockIdx.y == 0) lm_eval_general_pass<F32, NF32, COST, 0>(frames, edges, tiles, tile_len, corr, frame_gen, weight, robust, partial);
-  else if (blockIdx.y == 1) lm_eval_general_pass<F32, NF32, COST, 1>(frames, edges, tiles, tile_len, corr, frame_gen, weight, robust, partial);
-  else lm_eval_general_pass<F32, NF32, COST, 2>(frames, edges, tiles, tile_len, corr, frame_gen, weight, robust, partial);
+  __syncthreads();
+  if (threadIdx.x < 2 * GACC) {
+    const int rl = threadIdx.x / GACC, i = threadIdx.x - GACC * rl;
+    double v = 0.0;
+    for (int w = 0; w < EVAL_THREADS / 32; ++w) v += sred[w][rl][i];
+    // (rotation, translation) order -> the parameterisation's tangent order, then the 12x12 upper-triangle layout
+    auto real = [&](int a) { return (a + rot0) % 6; };
+    int dst = -1;
+    if (i < 21) {
+      int a = 0, rem = i; while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+      const int ra = real(a), rb = real(a + rem);
+      dst = u12(6 * rl + min(ra, rb), 6 * rl + max(ra, rb));
+    } else if (i < 39) {
+      const int a = (i - 21) / 6, b = (i - 21) - 6 * a;
+      dst = u12(real(rl ? 3 + a : a), 6 + real(b));
+    } else if (i < 45) dst = 78 + 6 * rl + real(i - 39);
+    else if (rl == 0) dst = 90;
+    if (dst >= 0) partial[(size_t)blockIdx.x * GBLK + dst] = v;
+  }
 }
 
 // general-path counterpart of lm_edge_kernel: the partials already are the pair matrix in the parameterisation tangent

@@ -639,9 +639,9 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
     // 11.1 -> 9.0 ms, round 1 6.6 -> 5.9 ms; from the second seeded round on the 32-byte AABB nodes win (4.57 vs 4.96 ms).
     // Poses set from outside since the last solve count as a fresh start.
     if (!seed || c->last_lm_iters == (1 << 20)) c->seeded_rounds = 0;
-    // A/B knob (flags bits 8-11 = n > 0): seeded rounds also count as far while the previous solve took >= n LM iterations
-    const int far_iters = (c->flags >> 8) & 15;
-    const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1 || (far_iters > 0 && c->last_lm_iters >= far_iters));
+    // (Keeping later seeded rounds on the oriented boxes while the solves still take >= 4 LM iterations: rounds 2-3 2.30 -> 2.98,
+    // 1.51 -> 2.11 ms, profiles/r2/s10_*.)
+    const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1);
     if (seed) ++c->seeded_rounds;
     const bool ww = !(c->flags & MVICP_FLAG_STEP_LOOP);
 #define MV_KNN_ARGS c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(), \
@@ -833,16 +833,17 @@ template <bool F32> static void launch_eval(mvicp_ctx* c, int cost, int robust, 
 #undef MV_EVAL
 }
 
-template <bool F32> static void launch_eval_general(mvicp_ctx* c, int cost, int robust, const int* done_flag) {
+template <bool F32> static void launch_eval_general(mvicp_ctx* c, int param, int cost, int robust, const int* done_flag) {
+  const int rot0 = param == PARAM_QUAT ? 0 : 3;   // tangent order: quaternion (rotation, translation), SE3 (translation, rotation)
   const int nt = c->n_eval_tiles;
   if (!nt) return;
 #define MV_EVALG(COSTK)                                                                                          \
-  if (F32 && c->nor_f32) lm_eval_general_kernel<F32, F32, COSTK><<<dim3(nt, 3), EVAL_THREADS, 0, c->stream>>>(        \
+  if (F32 && c->nor_f32) lm_eval_general_kernel<F32, F32, COSTK><<<nt, EVAL_THREADS, 0, c->stream>>>(        \
       c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
-      c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag); \
-  else lm_eval_general_kernel<F32, false, COSTK><<<dim3(nt, 3), EVAL_THREADS, 0, c->stream>>>(                        \
+      c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, rot0, c->d_partial.as<double>(), done_flag); \
+  else lm_eval_general_kernel<F32, false, COSTK><<<nt, EVAL_THREADS, 0, c->stream>>>(                        \
       c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_eval_tiles.as<Tile>(), c->eval_tile_len,       \
-      c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, c->d_partial.as<double>(), done_flag)
+      c->d_corr.as<int32_t>(), c->d_gen.as<FrameGen>(), c->d_weight.as<float>(), robust, rot0, c->d_partial.as<double>(), done_flag)
   if (cost == COST_P2P) { MV_EVALG(COST_P2P); } else if (cost == COST_P2PLANE) { MV_EVALG(COST_P2PLANE); } else { MV_EVALG(COST_MIXED); }
 #undef MV_EVALG
 }
@@ -940,7 +941,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   LmWork w{};
   w.S = c->d_state.as<LmState>(); w.edges = c->d_edges.as<EdgeDev>(); w.eout = c->d_eout.as<double>();
   w.host_flag = c->d_flag;
-  if (std::getenv("MVICP_STEP_PROFILE")) { RET(c->d_prof.reserve(sizeof(long long) * 16)); w.prof = c->d_prof.as<long long>(); }
+  if (std::getenv("MVICP_STEP_PROFILE")) { RET(c->d_prof.reserve(sizeof(long long) * 64)); w.prof = c->d_prof.as<long long>(); }
   c->nonrigid = poses_nonrigid(c->h_poses.data(), M);   // the mirror follows every solve and every mvicp_set_poses
   const bool general = c->nonrigid && param != PARAM_AA;
   if (general) { RET(c->d_gen.reserve(sizeof(FrameGen) * M)); RET(c->d_partial.reserve(sizeof(double) * GBLK * std::max<size_t>(1, c->n_eval_tiles))); }
@@ -974,7 +975,7 @@ int mvicp_optimize(mvicp_ctx* c, int32_t param, int32_t cost, int32_t robust, co
   auto issue = [&]() -> int {
     if ((int)c->eval_ev.size() < c->eval_ev_used + 2) { cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b)); c->eval_ev.push_back(a); c->eval_ev.push_back(b); }
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used], c->stream));
-    if (general) { if (c->f32) launch_eval_general<true>(c, cost, st.robust, done_flag); else launch_eval_general<false>(c, cost, st.robust, done_flag); }
+    if (general) { if (c->f32) launch_eval_general<true>(c, param, cost, st.robust, done_flag); else launch_eval_general<false>(c, param, cost, st.robust, done_flag); }
     else if (c->f32) launch_eval<true>(c, cost, st.robust, done_flag); else launch_eval<false>(c, cost, st.robust, done_flag);
     CU(cudaEventRecord(c->eval_ev[c->eval_ev_used + 1], c->stream));
     c->eval_ev_used += 2;
@@ -1353,10 +1354,10 @@ int mvicp_get_stats(mvicp_ctx* c, mvicp_stats* out) {
   return MVICP_OK;
 }
 // development aid: the 16 clock64() stamps lm_step_kernel left when MVICP_STEP_PROFILE=1 (0..7 phase boundaries, 8..10 Cholesky parts)
-int mvicp_debug_step_profile(mvicp_ctx* c, long long* out16) {
-  if (!c || !out16 || !c->d_prof.p) return fail(MVICP_ERR_STATE, "mvicp_debug_step_profile: run with MVICP_STEP_PROFILE=1");
+int mvicp_debug_step_profile(mvicp_ctx* c, long long* out64) {
+  if (!c || !out64 || !c->d_prof.p) return fail(MVICP_ERR_STATE, "mvicp_debug_step_profile: run with MVICP_STEP_PROFILE=1");
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpy(out16, c->d_prof.p, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out64, c->d_prof.p, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
   return MVICP_OK;
 }
 int mvicp_get_stream(mvicp_ctx* c, void** stream) { if (!c || !stream) return fail(MVICP_ERR_INVALID, "bad arguments"); *stream = (void*)c->stream; return MVICP_OK; }

@@ -141,7 +141,7 @@ def test_pairwise_known_answer(oracle, golden_dir, name, param, cost):
 
 
 @pytest.mark.parametrize("param", [PARAM_AA, PARAM_QUAT, PARAM_SE3])
-@pytest.mark.parametrize("cost", [COST_P2P, COST_P2PLANE])
+@pytest.mark.parametrize("cost", [COST_P2P, COST_P2PLANE, COST_MIXED])
 def test_real_bunny_nonrigid_poses(oracle, golden_dir, param, cost):
     """BASELINE config 1: the reference's own scans with their sample poses, which are NOT rigid (singular values
     1, 0.9957, 0.9957; SURVEY section 7).  The reference then runs its quaternion / SE3 functors on non-unit quaternions;

@@ -173,6 +173,7 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src, int = 32) {
   hostemu::yield(hostemu::AT_WARP);
   return r;
 }
+template <class T> inline T __shfl_xor_sync(unsigned m, T v, int lane_mask, int = 32) { return __shfl_sync(m, v, (hostemu::cur % 32) ^ lane_mask); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
