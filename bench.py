@@ -416,12 +416,12 @@ def run_ours(args, cfg):
     run_rounds(eng, max(3, args.warmup), "dev", stream)
     sampler = ClockSampler(dev); sampler.start(); time.sleep(0.3)
     barrier()
-    l0 = eng.stats()["kernel_launches"]
+    st0 = eng.stats(); l0 = st0["kernel_launches"]
     t0 = time.perf_counter()
     per, _ = run_rounds(eng, args.steps, "dev", stream)
     barrier()
     wall_total = time.perf_counter() - t0
-    l1 = eng.stats()["kernel_launches"]
+    st1 = eng.stats(); l1 = st1["kernel_launches"]
     final_poses = eng.get_poses()
     # e2e: same K rounds, poses cross the C ABI as host buffers every step
     barrier()
@@ -516,6 +516,8 @@ def run_ours(args, cfg):
                                "(setup_ms_excluded), as the reference keeps its clouds and KD-trees across rounds",
                        "incl_setup_value": 1e3 / ((e2e_ms + setup_s * 1e3) / K)},
                "gpu_launches": int(l1 - l0), "clocks": clocks,
+               "select_guess": {"rounds": int(st1["select_guess_rounds"] - st0["select_guess_rounds"]),
+                                "edge_misses": int(st1["select_guess_misses"] - st0["select_guess_misses"])},
                "roofline": roof_knn if dominant == "knn" else roof_lm, "roofline_knn": roof_knn, "roofline_lm": roof_lm,
                "time_share": share}
         if wall_mat is not None:

@@ -38,7 +38,9 @@ typedef struct {
   int32_t flags;        /* MVICP_FLAG_*                                                       */
   void*   stream;       /* cudaStream_t to run on (NULL: the context creates its own)         */
 } mvicp_config;
-enum { MVICP_FLAG_STEP_LOOP = 32, /* NN search: round 1's single loop of uniform steps instead of the while-while loop (csrc/knn.cuh
+enum { MVICP_FLAG_NO_SELECT_GUESS = 64, /* median select: always the three histogram passes, never the guess checked by the NN kernel's epilogue
+                                        (csrc/select.cuh) in rounds that follow a one-iteration solve */
+       MVICP_FLAG_STEP_LOOP = 32, /* NN search: round 1's single loop of uniform steps instead of the while-while loop (csrc/knn.cuh
                                       nn_drain); same matches, for A/B measurements */
        MVICP_FLAG_NO_ADJ = 8,     /* NN search: do not use the per-leaf neighbour lists (csrc/adjacency.h) that let a seeded query inside its
                                       start leaf's reach skip the tree walk; same matches, for A/B measurements */
@@ -88,6 +90,8 @@ typedef struct {                  /* device-side timings of the last mvicp_corre
   int64_t kernel_launches;        /* kernels of this library launched since mvicp_create */
   int64_t queries;                /* NN queries answered by the last correspond      */
   int64_t correspondences;        /* inliers after the cutoff, all local edges       */
+  int64_t select_guess_rounds;    /* mvicp_correspond calls whose median select was the guess checked by the NN kernel (csrc/select.cuh) */
+  int64_t select_guess_misses;    /* (edge, round) pairs in which that guess missed and the edge was redone from scratch */
 } mvicp_stats;
 
 void mvicp_default_lm_options(mvicp_lm_options* o);

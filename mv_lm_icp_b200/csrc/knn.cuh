@@ -263,14 +263,18 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
 
 // One thread per (edge, src point) query; src points are walked in the src frame's tree order so that the
 // lanes of a warp descend the dst tree together.
-template <bool F32, bool WW>
+// SEL: the epilogue also feeds the guessed median select (select.cuh): per edge, the number of inliers, the number of inliers
+// below the guessed window of keys, and the keys inside the window.
+template <bool F32, bool WW, bool SEL = false>
 __global__ void __launch_bounds__(KNN_TILE)
 knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
            const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
-           const int32_t* seed, double thresh) {
+           const int32_t* seed, double thresh, SelGuess sg, int gridDimEdges /* number of edges: stride of sg.win */) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ EdgeXf sx;
+  __shared__ unsigned int s_cnt[2];
+  if (SEL && threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
   {
     const double* g = reinterpret_cast<const double*>(xfs + t.edge);
     double* s = reinterpret_cast<double*>(&sx);
@@ -280,7 +284,9 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
   const FrameDev fs = frames[e.src];
   const FrameDev fd = frames[e.dst];
   const int ks = t.start + threadIdx.x;
-  if (ks >= e.n_src) return;
+  if (!SEL && ks >= e.n_src) return;
+  bool inlier = false; double best = 0.0;
+  if (ks < e.n_src) {
   double px, py, pz; int orig;
   Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
   // g = R_s p + t_s
@@ -300,10 +306,23 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
     if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
   }
   nn_search<F32, NNQuery, WW>(fd, nq, start_leaf);
-  const double best = nq.best; const int bi = nq.bi;
-  const bool inlier = __dsqrt_rn(best) < thresh;
+  best = nq.best; const int bi = nq.bi;
+  inlier = __dsqrt_rn(best) < thresh;
   corr[e.off + orig] = inlier ? bi : ~bi;
   d2out[e.off + orig] = best;
+  }
+  if (SEL) {   // every thread of the CTA arrives here
+    const unsigned long long key = (unsigned long long)__double_as_longlong(best);
+    const unsigned long long lo = sg.win[t.edge], hi = sg.win[(size_t)gridDimEdges + t.edge];
+    const unsigned int m_in = __ballot_sync(0xffffffffu, inlier), m_lo = __ballot_sync(0xffffffffu, inlier && key < lo);
+    if ((threadIdx.x & 31) == 0) { if (m_in) atomicAdd(&s_cnt[0], (unsigned int)__popc(m_in)); if (m_lo) atomicAdd(&s_cnt[1], (unsigned int)__popc(m_lo)); }
+    if (inlier && key >= lo && key < hi) {
+      const unsigned int slot = atomicAdd(&sg.cand_n[t.edge], 1u);
+      if (slot < (unsigned int)SEL_CAP) sg.cand[(size_t)t.edge * SEL_CAP + slot] = key;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { if (s_cnt[0]) atomicAdd(&sg.total[t.edge], s_cnt[0]); if (s_cnt[1]) atomicAdd(&sg.below[t.edge], s_cnt[1]); }
+  }
 }
 
 template <bool F32>

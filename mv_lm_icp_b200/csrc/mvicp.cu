@@ -97,6 +97,10 @@ struct mvicp_ctx {
   std::vector<EdgeDev> h_edges;
   std::vector<int32_t> edge_owner;   // rank that processes edge e (-1: src frame fixed, nobody)
   DevBuf d_edges, d_xf, d_corr, d_d2, d_count, d_sel, d_hist, d_weight, d_median, d_selcand, d_selcand_n;
+  DevBuf d_sel_cnt;            // guessed select: [E] inliers | [E] inliers below the guessed window | [1] guesses that missed
+  DevBuf d_sel_win;            // [3E] window lo | hi | log2 half-width (select.cuh)
+  bool sel_valid = false;      // d_sel holds the previous round's medians (a select ran since the buffers were laid out)
+  int64_t sel_guess_rounds = 0;
   DevBuf d_knn_tiles, d_eval_tiles, d_edge_tile_begin, d_partial;
   int n_knn_tiles = 0, n_eval_tiles = 0, eval_tile_len = EVAL_TILE;
   int64_t total_slots = 0;
@@ -369,7 +373,7 @@ void mvicp_destroy(mvicp_ctx* c) {
   if (c->comm) ncclCommDestroy(c->comm);
   for (void* p : c->frame_allocs) cudaFree(p);
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
-                    &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
+                    &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_sel_cnt, &c->d_sel_win, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
@@ -569,6 +573,10 @@ static int rebuild_work(mvicp_ctx* c) {
   RET(c->d_median.reserve(sizeof(double) * E));
   RET(c->d_selcand.reserve(sizeof(unsigned long long) * SEL_CAP * (size_t)E));
   RET(c->d_selcand_n.reserve(sizeof(unsigned int) * E));
+  RET(c->d_sel_cnt.reserve(sizeof(unsigned int) * (2 * (size_t)E + 1)));
+  CU(cudaMemset(c->d_sel_cnt.p, 0, sizeof(unsigned int) * (2 * (size_t)E + 1)));
+  RET(c->d_sel_win.reserve(sizeof(unsigned long long) * 3 * (size_t)E));
+  c->sel_valid = false;
   CU(cudaMemset(c->d_hist.p, 0, sizeof(unsigned int) * SEL_BINS * (size_t)E));
   CU(cudaMemset(c->d_weight.p, 0, sizeof(float) * E));
   CU(cudaMemset(c->d_selcand_n.p, 0, sizeof(unsigned int) * E));
@@ -633,6 +641,7 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
   CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
+  bool guess = false;
   if (c->n_knn_tiles) {
     // Far rounds search the oriented-box node array (far.cuh): a round without seeds, and the first round that has them (its
     // seeds were found before the first LM solve moved the clouds by centimetres).  Measured on config 3 (profiles/r2): round 0
@@ -644,17 +653,31 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
     const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1);
     if (seed) ++c->seeded_rounds;
     const bool ww = !(c->flags & MVICP_FLAG_STEP_LOOP);
+    // A round that follows a one-iteration solve hardly moves anything: a window of keys around the previous median is a guess that
+    // the NN kernel's epilogue can check on the fly, which replaces the three passes of the select (select.cuh).
+    guess = seed && !far && ww && c->sel_valid && c->last_lm_iters <= 1 && !(c->flags & MVICP_FLAG_NO_SELECT_GUESS);
+    unsigned int* cnt = c->d_sel_cnt.as<unsigned int>();
+    const SelGuess sg = {c->d_sel_win.as<unsigned long long>(), cnt, cnt + E, c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>()};
 #define MV_KNN_ARGS c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(), \
                     c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh
     if (far && ww) knn_far_kernel<F32, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
     else if (far) knn_far_kernel<F32, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
-    else if (ww) knn_kernel<F32, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS);
-    else knn_kernel<F32, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS);
+    else if (guess) knn_kernel<F32, true, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, sg, E);
+    else if (ww) knn_kernel<F32, true, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, sg, E);
+    else knn_kernel<F32, false, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, sg, E);
 #undef MV_KNN_ARGS
   }
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->stats.kernel_launches += 1 + (c->n_knn_tiles ? 1 : 0);
   // exact median -> weight
+  if (guess) {
+    unsigned int* cnt = c->d_sel_cnt.as<unsigned int>();
+    select_guess_finish_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
+        c->d_sel.as<SelState>(), cnt, cnt + E, c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>(),
+        c->d_weight.as<float>(), c->d_median.as<double>(), c->d_count.as<unsigned long long>(), c->d_sel_win.as<unsigned long long>(), cnt + 2 * (size_t)E);
+    c->stats.kernel_launches += 1;
+    ++c->sel_guess_rounds;
+  } else {
   select_init_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_sel.as<SelState>(), E);
   c->stats.kernel_launches += 1;
   const int shifts[2] = {53, 42};
@@ -674,8 +697,11 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
         c->d_sel.as<SelState>(), c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>());
   select_finish_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
                                                          c->d_sel.as<SelState>(), c->d_selcand.as<unsigned long long>(),
-                                                         c->d_selcand_n.as<unsigned int>(), c->d_weight.as<float>(), c->d_median.as<double>());
+                                                         c->d_selcand_n.as<unsigned int>(), c->d_weight.as<float>(), c->d_median.as<double>(),
+                                                         c->d_sel_win.as<unsigned long long>());
   c->stats.kernel_launches += 1 + (c->n_eval_tiles ? 1 : 0);
+  }
+  c->sel_valid = true;
   CU(cudaEventRecord(c->ev[2], c->stream));
   CU(cudaGetLastError());
   return MVICP_OK;
@@ -1349,6 +1375,12 @@ int mvicp_get_stats(mvicp_ctx* c, mvicp_stats* out) {
   if (c->E && fetch_edge_meta(c) == MVICP_OK) {
     int64_t s = 0; for (int e = 0; e < c->E; ++e) if (c->h_edges[e].owned) s += (int64_t)c->h_count[e];
     c->stats.correspondences = s;
+  }
+  c->stats.select_guess_rounds = c->sel_guess_rounds;
+  if (c->d_sel_cnt.p && c->E) {
+    unsigned int miss = 0;
+    CU(cudaMemcpy(&miss, c->d_sel_cnt.as<unsigned int>() + 2 * (size_t)c->E, sizeof miss, cudaMemcpyDeviceToHost));
+    c->stats.select_guess_misses = miss;
   }
   *out = c->stats;
   return MVICP_OK;

@@ -57,4 +57,22 @@ struct EdgeXf { double Rs[9], ts[3], Rinv[9], td[3]; };
 
 struct Tile { int32_t edge; int32_t start; };   // work item: `count` slots of one edge from `start`
 
+// ---- median select (select.cuh); the NN kernel's epilogue feeds its guessed variant (knn.cuh) ----
+struct SelState {            // one per edge
+  unsigned long long prefix; // bits decided so far (high part)
+  unsigned long long rank;   // remaining rank inside the current prefix bucket
+  unsigned long long count;  // inliers of the edge
+};
+
+constexpr int SEL_CAP = 4096;   // collected candidates per edge
+
+// what the NN kernel's epilogue needs for the guessed select (all per edge)
+struct SelGuess {
+  const unsigned long long* win;  // [3E]: window [lo, hi) of keys around the previous median | log2 of its half-width
+  unsigned int* total;            // += inliers
+  unsigned int* below;            // += inliers whose key lies below the window
+  unsigned long long* cand;       // [SEL_CAP] keys inside the window
+  unsigned int* cand_n;
+};
+
 }  // namespace mv

@@ -5,7 +5,7 @@ import pytest
 
 from helpers import oracle_correspond, scene
 from mv_lm_icp_b200 import Engine, synth
-from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED, FLAG_STEP_LOOP
+from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED, FLAG_NO_SELECT_GUESS, FLAG_STEP_LOOP, default_options
 
 pytestmark = pytest.mark.gpu
 
@@ -171,6 +171,66 @@ def test_median_with_masses_of_near_equal_distances(oracle):
     edges = [(1, 0), (2, 0)]
     eng = Engine(); eng.set_frames(pts, None); eng.set_graph(edges); eng.set_poses([np.eye(4)] * 3)
     eng.correspond(0.05)
+    ref = oracle_correspond(oracle, pts, [np.eye(4)] * 3, edges, kind="brute")
+    _check_edges(eng, ref, edges)
+    eng.close()
+
+
+def _edge_meta(eng, edges):
+    return [eng.get_edge(e, arrays=False) for e in range(len(edges))]
+
+
+def test_guessed_median_select_is_exact(oracle):
+    """In a round that follows a one-iteration solve the NN kernel's epilogue checks the previous median's 22-bit prefix as a guess and
+    the three select passes are skipped (select.cuh).  Inlier counts and weights must be bit-identical to the full select: (a) on a
+    run that converges (guesses hit), (b) while the poses still jump (one LM iteration per round from the noisy start: guesses miss,
+    the edge is redone from scratch), and the final round is checked against the oracle."""
+    sc = scene(4, 5003, 21)
+    edges = synth.ring_edges(4, 2)
+    one = default_options(); one.max_num_iterations = 1
+    for warm in (8, 0):      # (a) 8 full solves first, then one-iteration rounds that barely move; (b) one-iteration rounds from the start
+        engs = [Engine(flags=f) for f in (0, FLAG_NO_SELECT_GUESS)]
+        for eng in engs:
+            eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
+        for rnd in range(warm + 6):
+            metas = []
+            for eng in engs:
+                eng.correspond(0.05)
+                metas.append(_edge_meta(eng, edges))
+                eng.optimize(options=None if rnd < warm else one)
+            for (c0, w0), (c1, w1) in zip(*metas):
+                assert c0 == c1 and np.float32(w0).view(np.uint32) == np.float32(w1).view(np.uint32), (rnd, c0, c1, w0, w1)
+        assert np.array_equal(engs[0].get_poses(), engs[1].get_poses())
+        st = [eng.stats() for eng in engs]
+        assert st[0]["select_guess_rounds"] >= 3 and st[1]["select_guess_rounds"] == 0, st
+        if warm:
+            assert st[0]["select_guess_misses"] <= 2, st[0]        # converged: the prefix hardly moves any more
+        else:
+            assert st[0]["select_guess_misses"] > 0, st[0]         # still moving: this run is the test of the fallback
+        poses = engs[0].get_poses()
+        engs[0].correspond(0.05)
+        ref = oracle_correspond(oracle, sc["pts"], poses, edges)
+        _check_edges(engs[0], ref, edges)
+        for eng in engs:
+            eng.close()
+
+
+def test_guessed_median_select_degenerate_buckets(oracle):
+    """The shell / all-equal clouds of the test above under the guessed select: the guessed bucket holds more keys than the candidate
+    buffer (miss by overflow -> scan of the edge), and the empty edge of a fixed src frame stays empty."""
+    rng = np.random.default_rng(9)
+    u = rng.normal(size=(6000, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    shell = (u * (0.01 * (1 + rng.uniform(0, 1e-5, size=(6000, 1))))).astype(np.float32).astype(np.float64)
+    same = np.tile(np.array([[0.0078125, 0.0, 0.0]]), (5000, 1))
+    pts = [np.zeros((1, 3)), shell, same]
+    edges = [(1, 0), (2, 0), (0, 1)]
+    none = default_options(); none.max_num_iterations = 0
+    eng = Engine(); eng.set_frames(pts, None); eng.set_graph(edges); eng.set_poses([np.eye(4)] * 3)
+    eng.correspond(0.05)
+    eng.optimize(cost=0, options=none)       # zero iterations: the poses stay, the next rounds count as converged
+    for _ in range(3):
+        eng.correspond(0.05)
+    assert eng.stats()["select_guess_rounds"] >= 1
     ref = oracle_correspond(oracle, pts, [np.eye(4)] * 3, edges, kind="brute")
     _check_edges(eng, ref, edges)
     eng.close()

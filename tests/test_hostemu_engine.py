@@ -58,6 +58,8 @@ def test_correspondence_step(emu, oracle, golden_dir):
     T.test_median_with_masses_of_near_equal_distances(oracle)
     T.test_closest_point_api(oracle)
     T.test_all_edges_in_one_call_equal_the_per_edge_lists(oracle)
+    T.test_guessed_median_select_is_exact(oracle)
+    T.test_guessed_median_select_degenerate_buckets(oracle)
 
 
 @pytest.mark.parametrize("param", [0, 1, 2])

@@ -135,6 +135,16 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta, int 
   hostemu::yield(hostemu::AT_WARP);
   return r;
 }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta, int = 32) {
+  static_assert(sizeof(T) <= 8, "shuffle of > 8 bytes");
+  const int w = hostemu::cur / 32, l = hostemu::cur % 32;
+  long long raw = 0; std::memcpy(&raw, &v, sizeof(T)); hostemu::warp_slot[w][l] = raw;
+  hostemu::yield(hostemu::AT_WARP);
+  const int src = l - (int)delta >= 0 ? l - (int)delta : l;
+  raw = hostemu::warp_slot[w][src]; T r; std::memcpy(&r, &raw, sizeof(T));
+  hostemu::yield(hostemu::AT_WARP);
+  return r;
+}
 inline int __any_sync(unsigned, int p) {
   const int w = hostemu::cur / 32, l = hostemu::cur % 32;
   hostemu::vote_slot[w][l] = p ? 1 : 0;
@@ -174,6 +184,7 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src, int = 32) {
   return r;
 }
 template <class T> inline T __shfl_xor_sync(unsigned m, T v, int lane_mask, int = 32) { return __shfl_sync(m, v, (hostemu::cur % 32) ^ lane_mask); }
+inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }

@@ -34,5 +34,9 @@ static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline float __fmul_ru(float a, float b) { return hs_up((double)a * (double)b); }
 static inline float __fmaf_ru(float a, float b, float c) { return std::nextafterf(hs_up((double)a * (double)b + (double)c), INFINITY); }
 static inline void __syncthreads() {}
+// declarations only, so that the kernels' text parses: the host check calls the search functions, never a kernel
+unsigned __ballot_sync(unsigned, int);
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+template <class T> T atomicAdd(T*, T);
 static inline void __syncwarp() {}
 static inline int __any_sync(unsigned, int p) { return p; }   // one-lane "warp"
