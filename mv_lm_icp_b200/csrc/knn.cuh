@@ -266,7 +266,7 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
 // SEL: the epilogue also feeds the guessed median select (select.cuh): per edge, the number of inliers, the number of inliers
 // below the guessed window of keys, and the keys inside the window.
 template <bool F32, bool WW, bool SEL = false>
-__global__ void __launch_bounds__(KNN_TILE)
+__global__ void __launch_bounds__(KNN_TILE, 5)   // 5 CTAs per SM = 48 registers: the SEL epilogue must not cost a CTA of occupancy
 knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
            const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
            const int32_t* seed, double thresh, SelGuess sg, int gridDimEdges /* number of edges: stride of sg.win */) {
