@@ -518,6 +518,9 @@ def run_ours(args, cfg):
                "gpu_launches": int(l1 - l0), "clocks": clocks,
                "select_guess": {"rounds": int(st1["select_guess_rounds"] - st0["select_guess_rounds"]),
                                 "edge_misses": int(st1["select_guess_misses"] - st0["select_guess_misses"])},
+               "certified_matches": {"rounds": int(st1["cert_rounds"] - st0["cert_rounds"]),
+                                     "kept_queries": int(st1["cert_reused"] - st0["cert_reused"]),
+                                     "kept_fraction_in_those_rounds": round((st1["cert_reused"] - st0["cert_reused"]) / max(1, (st1["cert_rounds"] - st0["cert_rounds"]) * st1["queries"]), 4)},
                "roofline": roof_knn if dominant == "knn" else roof_lm, "roofline_knn": roof_knn, "roofline_lm": roof_lm,
                "time_share": share}
         if wall_mat is not None:

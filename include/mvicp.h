@@ -38,7 +38,9 @@ typedef struct {
   int32_t flags;        /* MVICP_FLAG_*                                                       */
   void*   stream;       /* cudaStream_t to run on (NULL: the context creates its own)         */
 } mvicp_config;
-enum { MVICP_FLAG_NO_SELECT_GUESS = 64, /* median select: always the three histogram passes, never the guess checked by the NN kernel's epilogue
+enum { MVICP_FLAG_NO_CERT = 128,         /* NN search: never keep a match on the strength of the previous round's certificate (csrc/knn.cuh,
+                                        CERT): every query of every round is searched */
+       MVICP_FLAG_NO_SELECT_GUESS = 64, /* median select: always the three histogram passes, never the guess checked by the NN kernel's epilogue
                                         (csrc/select.cuh) in rounds that follow a one-iteration solve */
        MVICP_FLAG_STEP_LOOP = 32, /* NN search: round 1's single loop of uniform steps instead of the while-while loop (csrc/knn.cuh
                                       nn_drain); same matches, for A/B measurements */
@@ -92,6 +94,8 @@ typedef struct {                  /* device-side timings of the last mvicp_corre
   int64_t correspondences;        /* inliers after the cutoff, all local edges       */
   int64_t select_guess_rounds;    /* mvicp_correspond calls whose median select was the guess checked by the NN kernel (csrc/select.cuh) */
   int64_t select_guess_misses;    /* (edge, round) pairs in which that guess missed and the edge was redone from scratch */
+  int64_t cert_rounds;            /* mvicp_correspond calls that kept certified matches (csrc/knn.cuh, CERT) */
+  int64_t cert_reused;            /* queries answered that way, all local edges, since mvicp_create */
 } mvicp_stats;
 
 void mvicp_default_lm_options(mvicp_lm_options* o);

@@ -36,7 +36,8 @@ class Stats(C.Structure):
     _fields_ = [("knn_ms", C.c_float), ("select_ms", C.c_float), ("lm_eval_ms", C.c_float), ("lm_other_ms", C.c_float),
                 ("correspond_ms", C.c_float), ("optimize_ms", C.c_float),
                 ("kernel_launches", C.c_int64), ("queries", C.c_int64), ("correspondences", C.c_int64),
-                ("select_guess_rounds", C.c_int64), ("select_guess_misses", C.c_int64)]
+                ("select_guess_rounds", C.c_int64), ("select_guess_misses", C.c_int64),
+                ("cert_rounds", C.c_int64), ("cert_reused", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

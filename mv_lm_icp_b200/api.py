@@ -21,6 +21,7 @@ FLAG_NO_ADJ = 8
 FLAG_NO_OBB = 16
 FLAG_STEP_LOOP = 32
 FLAG_NO_SELECT_GUESS = 64
+FLAG_NO_CERT = 128
 
 
 def _p(a, t=C.c_double):

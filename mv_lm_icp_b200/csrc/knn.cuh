@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <limits.h>
+#include <type_traits>
 #include "adjacency.h"
 #include "types.cuh"
 
@@ -78,6 +79,47 @@ __device__ __forceinline__ void nn_tighten(NNQuery& s) {
   s.bound32 = __fmul_ru(__fmaf_ru(s.eaf, __fmaf_ru(2.0f, r, s.eaf), b), 1.000001f);
 }
 
+// ---- certificates (temporal coherence) ----------------------------------------------------------------------------------
+// A search can also report how far the runner-up is: the smallest fp32 screen value of any point other than the winner that it
+// looked at, and the smallest lower bound of anything it pruned (a box, a split plane, "outside the start leaf's reach").  With
+// the error model above, everything except the winner lies at a true distance >= sqrt(other)(1 - 2^-22) - ea, the winner at
+// sqrt(best): the difference is a MARGIN m.  If the query is later found within m/2 of where it was then (in the dst frame), the
+// winner is still the strictly nearest point: |q'-p_j| <= d1 + D < d2 - D <= |q'-p_k| for D < m/2 -- no search needed, only its
+// distance (knn_kernel, CERT).  A certificate is {where the query was (fp32), m}, 16 bytes per query, stored in the kernel's own
+// (tile) order: read and written coalesced, renewed whenever the query has to be searched again.
+struct NNQueryT : NNQuery {
+  float m1, m2;     // the two smallest screen values over all scanned points
+  float v1;         // screen value of the current winner
+  float lbmin;      // smallest lower bound among everything pruned
+};
+template <class Q> struct nn_track { static constexpr bool value = false; };
+template <> struct nn_track<NNQueryT> { static constexpr bool value = true; };
+
+__device__ __forceinline__ void nn_track_init(NNQueryT& s) {
+  const float inf = __int_as_float(0x7f800000);
+  s.m1 = inf; s.m2 = inf; s.v1 = inf; s.lbmin = inf;
+}
+template <class Q> __device__ __forceinline__ void nn_pruned(Q& s, float lb) {
+  if constexpr (nn_track<Q>::value) s.lbmin = fminf(s.lbmin, lb);
+}
+// r <= sqrt(b)
+__device__ __forceinline__ float sqrt_lower(float b) {
+#ifdef __CUDA_ARCH__
+  float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return __fmul_rd(r, 0.99999904632568359375f);
+#else
+  return __fmul_rd(sqrtf(b), 0.99999904632568359375f);
+#endif
+}
+// margin, rounded down (<= 0: no certificate).  The winner has to hold the smallest screen value itself; if another point does
+// (fp32 reordering of near-equal distances, or the winner scanned twice) that point counts as the runner-up.
+__device__ __forceinline__ float nn_margin(const NNQueryT& s) {
+  const float other = fminf(s.v1 == s.m1 ? s.m2 : s.m1, s.lbmin);
+  const float lo = __fsub_rd(__fmul_rd(sqrt_lower(other), 0.999999f), s.eaf);
+  const float hi = sqrt_upper(__double2float_ru(s.best));
+  return __fsub_rd(lo, __fmul_ru(hi, 1.000001f));
+}
+
 template <class Q>
 __device__ __forceinline__ float box_lb32(const Box* __restrict__ boxes, int node, const Q& s) {
   const float4* b = reinterpret_cast<const float4*>(boxes + node);
@@ -111,8 +153,16 @@ __device__ __forceinline__ void nn_leaf_step(const FrameDev& fd, int leaf, int s
   if (pos >= fd.n) return;   // padding leaf of the implicit tree (reachable only while the bound is still infinite)
   const float4 r0 = __ldg(fd.pts_sf + pos), r1 = __ldg(fd.pts_sf + pos + 1);
   const float d0 = pt_d32(r0, s), d1 = pt_d32(r1, s);
-  if (d0 <= s.bound32) nn_exact<F32>(fd, pos, r0, s);
-  if (d1 <= s.bound32) nn_exact<F32>(fd, pos + 1, r1, s);
+  if constexpr (nn_track<Q>::value) {
+    s.m2 = fminf(s.m2, fmaxf(s.m1, d0)); s.m1 = fminf(s.m1, d0);
+    s.m2 = fminf(s.m2, fmaxf(s.m1, d1)); s.m1 = fminf(s.m1, d1);
+    int before = s.bi;
+    if (d0 <= s.bound32) { nn_exact<F32>(fd, pos, r0, s); if (s.bi != before) { s.v1 = d0; before = s.bi; } }
+    if (d1 <= s.bound32) { nn_exact<F32>(fd, pos + 1, r1, s); if (s.bi != before) s.v1 = d1; }
+  } else {
+    if (d0 <= s.bound32) nn_exact<F32>(fd, pos, r0, s);
+    if (d1 <= s.bound32) nn_exact<F32>(fd, pos + 1, r1, s);
+  }
 }
 
 // Exact 1-NN.  start_leaf >= 0: the leaf holding a good guess (previous round's match); < 0: greedy descent.
@@ -136,15 +186,15 @@ __device__ __forceinline__ void nn_drain(const FrameDev& fd, Q& s, int* stk_n, f
       int leaf = -1;
       while (sp > 0) {
         --sp;
-        if (stk_lb[sp] > s.bound32) continue;
+        if (stk_lb[sp] > s.bound32) { nn_pruned(s, stk_lb[sp]); continue; }
         int node = stk_n[sp];
         while (node < L) {   // descend: nearer child first, the other one onto the stack
           const int c0 = 2 * node;
           const float l0 = lb_of(c0), l1 = lb_of(c0 + 1);
           const bool first0 = l0 <= l1;
           const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
-          if (ln > s.bound32) { node = -1; break; }
-          if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+          if (ln > s.bound32) { nn_pruned(s, ln); node = -1; break; }
+          if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; } else nn_pruned(s, lf);
           node = first0 ? c0 : c0 + 1;
         }
         if (node >= L) { leaf = node - L; break; }
@@ -159,7 +209,7 @@ __device__ __forceinline__ void nn_drain(const FrameDev& fd, Q& s, int* stk_n, f
       if (node < 0) {
         if (sp == 0) break;
         --sp;
-        if (stk_lb[sp] > s.bound32) continue;
+        if (stk_lb[sp] > s.bound32) { nn_pruned(s, stk_lb[sp]); continue; }
         node = stk_n[sp]; sub = 0;
       }
       if (node >= L) {
@@ -171,9 +221,9 @@ __device__ __forceinline__ void nn_drain(const FrameDev& fd, Q& s, int* stk_n, f
         const bool first0 = l0 <= l1;
         const float ln = first0 ? l0 : l1, lf = first0 ? l1 : l0;
         if (ln <= s.bound32) {
-          if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; }
+          if (lf <= s.bound32) { stk_n[sp] = first0 ? c0 + 1 : c0; stk_lb[sp] = lf; ++sp; } else nn_pruned(s, lf);
           node = first0 ? c0 : c0 + 1; sub = 0;
-        } else node = -1;
+        } else { nn_pruned(s, ln); node = -1; }
       }
     }
   }
@@ -192,10 +242,15 @@ __device__ __forceinline__ bool nn_adj_fast(const FrameDev& fd, Q& s, int start_
   const float e2 = fmaf(ez0, ez0, fmaf(ey0, ey0, ex0 * ex0));
   // e + r <= R_S, every operation rounded up; the error of e (query and box in fp32) is inside the allowance that bound32 carries
   if (!(__fadd_ru(sqrt_upper(e2), sqrt_upper(s.bound32)) <= __int_as_float(hd.x))) return false;
+  if constexpr (nn_track<Q>::value) {   // every leaf outside the list is further than R_S - e
+    const float t = __fsub_rd(__int_as_float(hd.x), sqrt_upper(e2));
+    nn_pruned(s, t > 0.f ? __fmul_rd(t, t) : 0.f);
+  }
   unsigned todo = 0u;
   for (int i = 0; i < hd.y; ++i) {
     const int t = __ldg(ap + 2 + i);
-    if (box_lb32(fd.boxes, L + t, s) <= s.bound32) todo |= 1u << i;
+    const float lb = box_lb32(fd.boxes, L + t, s);
+    if (lb <= s.bound32) todo |= 1u << i; else nn_pruned(s, lb);
   }
   while (todo) {
     const int i = __ffs(todo) - 1; todo &= todo - 1u;
@@ -245,9 +300,9 @@ __device__ __forceinline__ void nn_search(const FrameDev& fd, Q& s, int start_le
     const int axis = __float_as_int(face) & 3;
     const float qa = axis == 0 ? s.fx : (axis == 1 ? s.fy : s.fz);
     const float dpl = (sib & 1) ? face - qa : qa - face;
-    if (dpl > 0.f && dpl * dpl > s.bound32) continue;
+    if (dpl > 0.f && dpl * dpl > s.bound32) { nn_pruned(s, dpl * dpl); continue; }
     const float lb = box_lb32(fd.boxes, sib, s);
-    if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; }
+    if (lb <= s.bound32) { stk_n[sp] = sib; stk_lb[sp] = lb; ++sp; } else nn_pruned(s, lb);
   }
   nn_drain<F32, WW, Q>(fd, s, stk_n, stk_lb, sp, [&](int nd) { return box_lb32(fd.boxes, nd, s); });
 }
@@ -261,32 +316,12 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
   s.bound32 = __int_as_float(0x7f800000);
 }
 
-// One thread per (edge, src point) query; src points are walked in the src frame's tree order so that the
-// lanes of a warp descend the dst tree together.
-// SEL: the epilogue also feeds the guessed median select (select.cuh): per edge, the number of inliers, the number of inliers
-// below the guessed window of keys, and the keys inside the window.
-template <bool F32, bool WW, bool SEL = false>
-__global__ void __launch_bounds__(KNN_TILE, 5)   // 5 CTAs per SM = 48 registers: the SEL epilogue must not cost a CTA of occupancy
-knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
-           const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
-           const int32_t* seed, double thresh, SelGuess sg, int gridDimEdges /* number of edges: stride of sg.win */) {
-  const Tile t = tiles[blockIdx.x];
-  const EdgeDev e = edges[t.edge];
-  __shared__ EdgeXf sx;
-  __shared__ unsigned int s_cnt[2];
-  if (SEL && threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
-  {
-    const double* g = reinterpret_cast<const double*>(xfs + t.edge);
-    double* s = reinterpret_cast<double*>(&sx);
-    for (int i = threadIdx.x; i < (int)(sizeof(EdgeXf) / sizeof(double)); i += blockDim.x) s[i] = g[i];
-  }
-  __syncthreads();
-  const FrameDev fs = frames[e.src];
-  const FrameDev fd = frames[e.dst];
-  const int ks = t.start + threadIdx.x;
-  if (!SEL && ks >= e.n_src) return;
-  bool inlier = false; double best = 0.0;
-  if (ks < e.n_src) {
+// One (edge, src point) query: transform, seed, [certificate test], search, results.  MODE 0: always search; 1: keep the match if
+// the certificate allows it (returns 1), otherwise do nothing and return 0 -- the caller searches it later; 2: search (no test).
+template <bool F32, bool WW, int CERT, int MODE>
+__device__ __forceinline__ int knn_one(const FrameDev& fs, const FrameDev& fd, const EdgeXf& sx, const EdgeDev& e, int ks,
+                                       int32_t* corr, double* __restrict__ d2out, const int32_t* seed, double thresh,
+                                       float4* __restrict__ certs, bool& inlier, double& best) {
   double px, py, pz; int orig;
   Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
   // g = R_s p + t_s
@@ -298,30 +333,110 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
   const double qy = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[3], ex), __dmul_rn(sx.Rinv[4], ey)), __dmul_rn(sx.Rinv[5], ez));
   const double qz = __dadd_rn(__dadd_rn(__dmul_rn(sx.Rinv[6], ex), __dmul_rn(sx.Rinv[7], ey)), __dmul_rn(sx.Rinv[8], ez));
 
-  NNQuery nq; nn_query_init(nq, qx, qy, qz, fd.absmax);
-  int start_leaf = -1;
+  typedef typename std::conditional<CERT != 0, NNQueryT, NNQuery>::type QT;
+  QT nq; nn_query_init(nq, qx, qy, qz, fd.absmax);
+  int start_leaf = -1, si = -1;
   if (seed) {   // previous round's match: a valid first guess, the search stays exact
     const int sd = seed[e.off + orig];
-    const int si = sd >= 0 ? sd : ~sd;
-    if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF;
+    si = sd >= 0 ? sd : ~sd;
+    if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF; else si = -1;
   }
-  nn_search<F32, NNQuery, WW>(fd, nq, start_leaf);
+  if constexpr (MODE == 1) {
+    // displacement since the certificate, rounded up, + the fp32 rounding of both positions (eaf covers it many times over)
+    const float4 ct = certs[e.off + ks];
+    const float dx = nq.fx - ct.x, dy = nq.fy - ct.y, dz = nq.fz - ct.z;
+    const float disp = __fadd_ru(__fmul_ru(sqrt_upper(__fmaf_ru(dz, dz, __fmaf_ru(dy, dy, __fmul_ru(dx, dx)))), 1.000001f), nq.eaf);
+    if (!(si >= 0 && __fmul_ru(2.0f, disp) < ct.w)) return 0;
+    // the previous match is still strictly nearer than anything else; its distance in the reference's operations
+    double mx, my, mz; int dummy;
+    Rec<F32>::load(fd.pts_o, si, mx, my, mz, dummy);
+    nq.best = d2_rn(qx, qy, qz, mx, my, mz); nq.bi = si;
+  } else {
+    if constexpr (CERT != 0) nn_track_init(nq);
+    nn_search<F32, QT, WW>(fd, nq, start_leaf);
+    if constexpr (CERT != 0) certs[e.off + ks] = make_float4(nq.fx, nq.fy, nq.fz, nn_margin(nq));
+  }
   best = nq.best; const int bi = nq.bi;
   inlier = __dsqrt_rn(best) < thresh;
   corr[e.off + orig] = inlier ? bi : ~bi;
   d2out[e.off + orig] = best;
+  return 1;
+}
+
+// what a finished query contributes to the guessed median select; every lane of the warp calls it (`done` = has a result)
+__device__ __forceinline__ void knn_sel_account(const SelGuess& sg, int edge, int n_edges, bool done, bool inlier, double best, unsigned int* s_cnt) {
+  const unsigned long long key = (unsigned long long)__double_as_longlong(best);
+  const unsigned long long lo = sg.win[edge], hi = sg.win[(size_t)n_edges + edge];
+  const bool in = done && inlier;
+  const unsigned int m_in = __ballot_sync(0xffffffffu, in), m_lo = __ballot_sync(0xffffffffu, in && key < lo);
+  if ((threadIdx.x & 31) == 0) { if (m_in) atomicAdd(&s_cnt[0], (unsigned int)__popc(m_in)); if (m_lo) atomicAdd(&s_cnt[1], (unsigned int)__popc(m_lo)); }
+  if (in && key >= lo && key < hi) {
+    const unsigned int slot = atomicAdd(&sg.cand_n[edge], 1u);
+    if (slot < (unsigned int)SEL_CAP) sg.cand[(size_t)edge * SEL_CAP + slot] = key;
+  }
+}
+
+// One thread per (edge, src point) query; src points are walked in the src frame's tree order so that the
+// lanes of a warp descend the dst tree together.
+// SEL: the epilogue also feeds the guessed median select (select.cuh): per edge, the number of inliers, the number of inliers
+// below the guessed window of keys, and the keys inside the window.
+// CERT (needs seeds): 1 = every query is searched and leaves a certificate {its position, the margin by which its match beats
+// everything else (nn_margin)}; 2 = a query that is still within half its margin of the certified position keeps its match and only
+// recomputes the distance; the others are collected per CTA and searched (and re-certified) by as few warps as they fill, so that a
+// handful of them does not make every warp of the CTA walk the tree.  reused[edge] counts the kept ones.
+template <bool F32, bool WW, bool SEL = false, int CERT = 0>
+__global__ void __launch_bounds__(KNN_TILE, 5)   // 5 CTAs per SM = 48 registers: the SEL epilogue must not cost a CTA of occupancy
+knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
+           const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
+           const int32_t* seed, double thresh, SelGuess sg, int n_edges /* stride of sg.win */,
+           float4* __restrict__ certs, unsigned long long* __restrict__ reused /* per edge */) {
+  static_assert(CERT != 2 || SEL, "certified reuse runs in converged rounds, together with the guessed select");
+  const Tile t = tiles[blockIdx.x];
+  const EdgeDev e = edges[t.edge];
+  __shared__ EdgeXf sx;
+  __shared__ unsigned int s_cnt[4];            // inliers | inliers below the window | kept by certificate | to be searched
+  __shared__ unsigned short s_list[CERT == 2 ? KNN_TILE : 1];
+  if ((SEL || CERT == 2) && threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+  {
+    const double* g = reinterpret_cast<const double*>(xfs + t.edge);
+    double* s = reinterpret_cast<double*>(&sx);
+    for (int i = threadIdx.x; i < (int)(sizeof(EdgeXf) / sizeof(double)); i += blockDim.x) s[i] = g[i];
+  }
+  __syncthreads();
+  const FrameDev fs = frames[e.src];
+  const FrameDev fd = frames[e.dst];
+  const int ks = t.start + threadIdx.x;
+  if (!SEL && ks >= e.n_src) return;
+  bool inlier = false; double best = 0.0;
+  if constexpr (CERT == 2) {
+    int kept = 0;
+    if (ks < e.n_src) {
+      kept = knn_one<F32, WW, CERT, 1>(fs, fd, sx, e, ks, corr, d2out, seed, thresh, certs, inlier, best);
+      if (!kept) s_list[atomicAdd(&s_cnt[3], 1u)] = (unsigned short)threadIdx.x;
+    }
+    knn_sel_account(sg, t.edge, n_edges, kept != 0, inlier, best, s_cnt);
+    const unsigned int mk = __ballot_sync(0xffffffffu, kept != 0);
+    if ((threadIdx.x & 31) == 0 && mk) atomicAdd(&s_cnt[2], (unsigned int)__popc(mk));
+    __syncthreads();
+    const int n_todo = (int)s_cnt[3];
+    for (int base = threadIdx.x & ~31; base < n_todo; base += blockDim.x) {      // warp-uniform trip count
+      const int i = base + (threadIdx.x & 31);
+      const bool has = i < n_todo;
+      if (has) knn_one<F32, WW, CERT, 2>(fs, fd, sx, e, t.start + (int)s_list[i], corr, d2out, seed, thresh, certs, inlier, best);
+      knn_sel_account(sg, t.edge, n_edges, has, inlier, best, s_cnt);
+    }
+  } else {
+    const bool has = ks < e.n_src;
+    if (has) knn_one<F32, WW, CERT, 0>(fs, fd, sx, e, ks, corr, d2out, seed, thresh, certs, inlier, best);
+    if (SEL) knn_sel_account(sg, t.edge, n_edges, has, inlier, best, s_cnt);
   }
   if (SEL) {   // every thread of the CTA arrives here
-    const unsigned long long key = (unsigned long long)__double_as_longlong(best);
-    const unsigned long long lo = sg.win[t.edge], hi = sg.win[(size_t)gridDimEdges + t.edge];
-    const unsigned int m_in = __ballot_sync(0xffffffffu, inlier), m_lo = __ballot_sync(0xffffffffu, inlier && key < lo);
-    if ((threadIdx.x & 31) == 0) { if (m_in) atomicAdd(&s_cnt[0], (unsigned int)__popc(m_in)); if (m_lo) atomicAdd(&s_cnt[1], (unsigned int)__popc(m_lo)); }
-    if (inlier && key >= lo && key < hi) {
-      const unsigned int slot = atomicAdd(&sg.cand_n[t.edge], 1u);
-      if (slot < (unsigned int)SEL_CAP) sg.cand[(size_t)t.edge * SEL_CAP + slot] = key;
-    }
     __syncthreads();
-    if (threadIdx.x == 0) { if (s_cnt[0]) atomicAdd(&sg.total[t.edge], s_cnt[0]); if (s_cnt[1]) atomicAdd(&sg.below[t.edge], s_cnt[1]); }
+    if (threadIdx.x == 0) {
+      if (s_cnt[0]) atomicAdd(&sg.total[t.edge], s_cnt[0]);
+      if (s_cnt[1]) atomicAdd(&sg.below[t.edge], s_cnt[1]);
+      if (CERT == 2 && s_cnt[2]) atomicAdd(&reused[t.edge], (unsigned long long)s_cnt[2]);
+    }
   }
 }
 

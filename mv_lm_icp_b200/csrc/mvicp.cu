@@ -99,6 +99,9 @@ struct mvicp_ctx {
   DevBuf d_edges, d_xf, d_corr, d_d2, d_count, d_sel, d_hist, d_weight, d_median, d_selcand, d_selcand_n;
   DevBuf d_sel_cnt;            // guessed select: [E] inliers | [E] inliers below the guessed window | [1] guesses that missed
   DevBuf d_sel_win;            // [3E] window lo | hi | log2 half-width (select.cuh)
+  DevBuf d_certs, d_cert_cnt;  // certificates (knn.cuh, CERT): {position, margin} per slot in tile order; reused queries per edge
+  bool cert_valid = false;     // every slot's margin belongs to the match in d_corr (the last mvicp_correspond ran with certificates)
+  int64_t cert_rounds = 0;
   bool sel_valid = false;      // d_sel holds the previous round's medians (a select ran since the buffers were laid out)
   int64_t sel_guess_rounds = 0;
   DevBuf d_knn_tiles, d_eval_tiles, d_edge_tile_begin, d_partial;
@@ -373,7 +376,7 @@ void mvicp_destroy(mvicp_ctx* c) {
   if (c->comm) ncclCommDestroy(c->comm);
   for (void* p : c->frame_allocs) cudaFree(p);
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
-                    &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_sel_cnt, &c->d_sel_win, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
+                    &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_sel_cnt, &c->d_sel_win, &c->d_certs, &c->d_cert_cnt, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
@@ -576,6 +579,10 @@ static int rebuild_work(mvicp_ctx* c) {
   RET(c->d_sel_cnt.reserve(sizeof(unsigned int) * (2 * (size_t)E + 1)));
   CU(cudaMemset(c->d_sel_cnt.p, 0, sizeof(unsigned int) * (2 * (size_t)E + 1)));
   RET(c->d_sel_win.reserve(sizeof(unsigned long long) * 3 * (size_t)E));
+  RET(c->d_certs.reserve(sizeof(float4) * off));
+  RET(c->d_cert_cnt.reserve(sizeof(unsigned long long) * E));
+  CU(cudaMemset(c->d_cert_cnt.p, 0, sizeof(unsigned long long) * E));
+  c->cert_valid = false;
   c->sel_valid = false;
   CU(cudaMemset(c->d_hist.p, 0, sizeof(unsigned int) * SEL_BINS * (size_t)E));
   CU(cudaMemset(c->d_weight.p, 0, sizeof(float) * E));
@@ -638,33 +645,48 @@ int mvicp_get_graph(mvicp_ctx* c, int32_t* E, int32_t* src, int32_t* dst) {
 }  // extern "C"
 template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   const int E = c->E;
-  edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
-  CU(cudaEventRecord(c->ev[0], c->stream));
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
-  bool guess = false;
+  bool guess = false, far = false;
+  int cert = 0;
+  const bool ww = !(c->flags & MVICP_FLAG_STEP_LOOP);
   if (c->n_knn_tiles) {
     // Far rounds search the oriented-box node array (far.cuh): a round without seeds, and the first round that has them (its
     // seeds were found before the first LM solve moved the clouds by centimetres).  Measured on config 3 (profiles/r2): round 0
     // 11.1 -> 9.0 ms, round 1 6.6 -> 5.9 ms; from the second seeded round on the 32-byte AABB nodes win (4.57 vs 4.96 ms).
     // Poses set from outside since the last solve count as a fresh start.
-    if (!seed || c->last_lm_iters == (1 << 20)) c->seeded_rounds = 0;
     // (Keeping later seeded rounds on the oriented boxes while the solves still take >= 4 LM iterations: rounds 2-3 2.30 -> 2.98,
     // 1.51 -> 2.11 ms, profiles/r2/s10_*.)
-    const bool far = c->obb_ready && (!seed || c->seeded_rounds < 1);
+    if (!seed || c->last_lm_iters == (1 << 20)) c->seeded_rounds = 0;
+    far = c->obb_ready && (!seed || c->seeded_rounds < 1);
     if (seed) ++c->seeded_rounds;
-    const bool ww = !(c->flags & MVICP_FLAG_STEP_LOOP);
     // A round that follows a one-iteration solve hardly moves anything: a window of keys around the previous median is a guess that
-    // the NN kernel's epilogue can check on the fly, which replaces the three passes of the select (select.cuh).
-    guess = seed && !far && ww && c->sel_valid && c->last_lm_iters <= 1 && !(c->flags & MVICP_FLAG_NO_SELECT_GUESS);
+    // the NN kernel's epilogue can check on the fly, which replaces the three passes of the select (select.cuh) ...
+    const bool steady = seed && !far && ww, converged = steady && c->last_lm_iters <= 1;
+    guess = converged && c->sel_valid && !(c->flags & MVICP_FLAG_NO_SELECT_GUESS);
+    // ... and most queries need no search at all: the previous search left a margin by which its match beats every other point,
+    // and the query is still within half of it of where it was (knn.cuh, CERT).  Certificates are written by the rounds that lead up to that
+    // (the previous solve took <= 3 iterations) and stay valid only while every round keeps them current.
+    if (steady && !(c->flags & MVICP_FLAG_NO_CERT)) cert = (guess && c->cert_valid) ? 2 : (c->last_lm_iters <= 3 ? 1 : 0);
+  }
+  edge_xf_kernel<<<(E + 127) / 128, 128, 0, c->stream>>>(c->d_poses.as<double>(), c->d_edges.as<EdgeDev>(), E, c->d_xf.as<EdgeXf>());
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  if (c->n_knn_tiles) {
     unsigned int* cnt = c->d_sel_cnt.as<unsigned int>();
     const SelGuess sg = {c->d_sel_win.as<unsigned long long>(), cnt, cnt + E, c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>()};
 #define MV_KNN_ARGS c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(), \
                     c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh
+#define MV_KNN_TAIL sg, E, c->d_certs.as<float4>(), c->d_cert_cnt.as<unsigned long long>()
     if (far && ww) knn_far_kernel<F32, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
     else if (far) knn_far_kernel<F32, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
-    else if (guess) knn_kernel<F32, true, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, sg, E);
-    else if (ww) knn_kernel<F32, true, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, sg, E);
-    else knn_kernel<F32, false, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, sg, E);
+    else if (cert == 2) knn_kernel<F32, true, true, 2><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
+    else if (guess && cert == 1) knn_kernel<F32, true, true, 1><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
+    else if (guess) knn_kernel<F32, true, true, 0><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
+    else if (cert == 1) knn_kernel<F32, true, false, 1><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
+    else if (ww) knn_kernel<F32, true, false, 0><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
+    else knn_kernel<F32, false, false, 0><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
+    c->cert_valid = cert != 0;
+    if (cert == 2) ++c->cert_rounds;
+#undef MV_KNN_TAIL
 #undef MV_KNN_ARGS
   }
   CU(cudaEventRecord(c->ev[1], c->stream));
@@ -812,6 +834,7 @@ int mvicp_set_edge(mvicp_ctx* c, int32_t e, const int32_t* first, const int32_t*
   CU(cudaMemcpy(c->d_weight.as<float>() + e, &weight, sizeof(float), cudaMemcpyHostToDevice));
   const unsigned long long cnt = (unsigned long long)count;
   CU(cudaMemcpy(c->d_count.as<unsigned long long>() + e, &cnt, sizeof cnt, cudaMemcpyHostToDevice));
+  c->cert_valid = false;   // the matches in d_corr are no longer the ones the certificates were written for
   return MVICP_OK;
 }
 
@@ -1377,6 +1400,13 @@ int mvicp_get_stats(mvicp_ctx* c, mvicp_stats* out) {
     c->stats.correspondences = s;
   }
   c->stats.select_guess_rounds = c->sel_guess_rounds;
+  c->stats.cert_rounds = c->cert_rounds;
+  if (c->d_cert_cnt.p && c->E) {
+    std::vector<unsigned long long> h(c->E);
+    CU(cudaMemcpy(h.data(), c->d_cert_cnt.p, sizeof(unsigned long long) * c->E, cudaMemcpyDeviceToHost));
+    int64_t s = 0; for (unsigned long long v : h) s += (int64_t)v;
+    c->stats.cert_reused = s;
+  }
   if (c->d_sel_cnt.p && c->E) {
     unsigned int miss = 0;
     CU(cudaMemcpy(&miss, c->d_sel_cnt.as<unsigned int>() + 2 * (size_t)c->E, sizeof miss, cudaMemcpyDeviceToHost));

@@ -5,7 +5,7 @@ import pytest
 
 from helpers import oracle_correspond, scene
 from mv_lm_icp_b200 import Engine, synth
-from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED, FLAG_NO_SELECT_GUESS, FLAG_STEP_LOOP, default_options
+from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED, FLAG_NO_CERT, FLAG_NO_SELECT_GUESS, FLAG_STEP_LOOP, default_options
 
 pytestmark = pytest.mark.gpu
 
@@ -213,6 +213,78 @@ def test_guessed_median_select_is_exact(oracle):
         _check_edges(engs[0], ref, edges)
         for eng in engs:
             eng.close()
+
+
+def test_certified_matches_are_exact(oracle):
+    """Converged rounds keep a query's previous match without searching when the previous search left a margin -- its match beats
+    every other point by m -- and the edge has moved by less than m/2 since (knn.cuh, CERT).  Matches and distances must be
+    bit-identical to searching every query: (a) after a run of full solves, with the poses then standing still (every query with a
+    positive margin is kept), (b) with one LM iteration per round from the noisy start, where the clouds keep moving by more than
+    many margins (those queries are collected per CTA, searched and re-certified); the final round is checked against the oracle."""
+    sc = scene(4, 5003, 21)
+    edges = synth.ring_edges(4, 2)
+    one = default_options(); one.max_num_iterations = 1
+    none = default_options(); none.max_num_iterations = 0
+    for warm, late in ((8, none), (0, one)):
+        engs = [Engine(flags=f) for f in (0, FLAG_NO_CERT, FLAG_NO_CERT | FLAG_NO_SELECT_GUESS)]
+        for eng in engs:
+            eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
+        for rnd in range(warm + 7):
+            nn = []
+            for eng in engs:
+                eng.correspond(0.05)
+                nn.append([eng.get_nn(e) for e in range(len(edges)) if edges[e][0] != 0] + [_edge_meta(eng, edges)])
+                eng.optimize(options=None if rnd < warm else late)
+            for other in nn[1:]:
+                for (i0, d0), (i1, d1) in zip(nn[0][:-1], other[:-1]):
+                    assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64)), rnd
+                assert nn[0][-1] == other[-1], rnd
+        for eng in engs[1:]:
+            assert np.array_equal(engs[0].get_poses(), eng.get_poses())
+        st = [eng.stats() for eng in engs]
+        n_q = st[0]["queries"]
+        assert st[0]["cert_rounds"] >= 3 and st[1]["cert_rounds"] == 0 and st[1]["cert_reused"] == 0, st
+        frac = st[0]["cert_reused"] / (n_q * st[0]["cert_rounds"])
+        if warm:
+            assert frac > 0.9, st[0]             # the poses stand still: kept unless a pruned box sat just outside the bound (tiny margin)
+        else:
+            assert 0 < frac < 0.5, st[0]         # still moving by more than most margins: those queries are searched again
+        poses = engs[0].get_poses()
+        engs[0].correspond(0.05)
+        ref = oracle_correspond(oracle, sc["pts"], poses, edges)
+        _check_edges(engs[0], ref, edges)
+        for eng in engs:
+            eng.close()
+
+
+def test_certificates_with_ties_and_duplicates(oracle):
+    """Exact ties never certify: a dst cloud in which every point exists twice (the lower index must win every round), queried
+    by a copy of itself moved by a rigid transform that the solve then removes."""
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-0.1, 0.1, size=(3000, 3)).astype(np.float32).astype(np.float64)
+    dup = np.concatenate([base, base[::-1]])
+    nor = np.tile(np.array([[0.0, 0.0, -1.0]]), (6000, 1))
+    pts = [dup, base.copy()]; nors = [nor, nor[:3000]]
+    edges = [(1, 0), (0, 1)]
+    P = [np.eye(4), np.eye(4)]; P[1][:3, 3] = [1e-4, -2e-4, 1e-4]
+    none = default_options(); none.max_num_iterations = 0
+    engs = [Engine(flags=f) for f in (0, FLAG_NO_CERT)]
+    res = []
+    for eng in engs:
+        eng.set_frames(pts, nors); eng.set_graph(edges); eng.set_poses(P)
+        eng.correspond(0.05); eng.optimize(cost=0, options=none)
+        out = []
+        for _ in range(4):
+            eng.correspond(0.05); out.append(eng.get_nn(0))
+        res.append(out)
+    for (i0, d0), (i1, d1) in zip(*res):
+        assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64))
+    idx = res[0][-1][0]
+    assert np.array_equal(idx, np.arange(3000))           # of the two copies the lower index
+    st = engs[0].stats()
+    assert st["cert_rounds"] >= 1 and st["cert_reused"] == 0, st   # every margin is zero
+    for eng in engs:
+        eng.close()
 
 
 def test_guessed_median_select_degenerate_buckets(oracle):

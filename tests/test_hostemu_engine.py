@@ -60,6 +60,8 @@ def test_correspondence_step(emu, oracle, golden_dir):
     T.test_all_edges_in_one_call_equal_the_per_edge_lists(oracle)
     T.test_guessed_median_select_is_exact(oracle)
     T.test_guessed_median_select_degenerate_buckets(oracle)
+    T.test_certified_matches_are_exact(oracle)
+    T.test_certificates_with_ties_and_duplicates(oracle)
 
 
 @pytest.mark.parametrize("param", [0, 1, 2])

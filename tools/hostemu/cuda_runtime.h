@@ -209,7 +209,11 @@ inline float hs_up(double v) { float f = (float)v; if ((double)f < v) f = std::n
 inline float __double2float_ru(double a) { return hs_up(a); }
 inline float __fsqrt_ru(float a) { return std::nextafterf(hs_up(std::sqrt((double)a)), INFINITY); }
 inline float __fadd_ru(float a, float b) { return hs_up((double)a + (double)b); }
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 inline float __fmul_ru(float a, float b) { return hs_up((double)a * (double)b); }
+inline float hs_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
+inline float __fmul_rd(float a, float b) { return hs_down((double)a * (double)b); }
+inline float __fsub_rd(float a, float b) { return hs_down((double)a - (double)b); }
 inline float __fmaf_ru(float a, float b, float c) { return std::nextafterf(hs_up((double)a * (double)b + (double)c), INFINITY); }
 inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 
