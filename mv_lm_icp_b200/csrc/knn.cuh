@@ -380,23 +380,18 @@ __device__ __forceinline__ void knn_sel_account(const SelGuess& sg, int edge, in
 // lanes of a warp descend the dst tree together.
 // SEL: the epilogue also feeds the guessed median select (select.cuh): per edge, the number of inliers, the number of inliers
 // below the guessed window of keys, and the keys inside the window.
-// CERT (needs seeds): 1 = every query is searched and leaves a certificate {its position, the margin by which its match beats
-// everything else (nn_margin)}; 2 = a query that is still within half its margin of the certified position keeps its match and only
-// recomputes the distance; the others are collected per CTA and searched (and re-certified) by as few warps as they fill, so that a
-// handful of them does not make every warp of the CTA walk the tree.  reused[edge] counts the kept ones.
+// CERT = 1 (needs seeds): every query also leaves a certificate {its position, the margin by which its match beats everything
+// else (nn_margin)} for the certified rounds that follow (knn_cert_kernel).
 template <bool F32, bool WW, bool SEL = false, int CERT = 0>
 __global__ void __launch_bounds__(KNN_TILE, 5)   // 5 CTAs per SM = 48 registers: the SEL epilogue must not cost a CTA of occupancy
 knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
            const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
-           const int32_t* seed, double thresh, SelGuess sg, int n_edges /* stride of sg.win */,
-           float4* __restrict__ certs, unsigned long long* __restrict__ reused /* per edge */) {
-  static_assert(CERT != 2 || SEL, "certified reuse runs in converged rounds, together with the guessed select");
+           const int32_t* seed, double thresh, SelGuess sg, int n_edges /* stride of sg.win */, float4* __restrict__ certs) {
   const Tile t = tiles[blockIdx.x];
   const EdgeDev e = edges[t.edge];
   __shared__ EdgeXf sx;
-  __shared__ unsigned int s_cnt[4];            // inliers | inliers below the window | kept by certificate | to be searched
-  __shared__ unsigned short s_list[CERT == 2 ? KNN_TILE : 1];
-  if ((SEL || CERT == 2) && threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+  __shared__ unsigned int s_cnt[2];            // inliers | inliers below the window
+  if (SEL && threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
   {
     const double* g = reinterpret_cast<const double*>(xfs + t.edge);
     double* s = reinterpret_cast<double*>(&sx);
@@ -408,34 +403,98 @@ knn_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edge
   const int ks = t.start + threadIdx.x;
   if (!SEL && ks >= e.n_src) return;
   bool inlier = false; double best = 0.0;
-  if constexpr (CERT == 2) {
-    int kept = 0;
-    if (ks < e.n_src) {
-      kept = knn_one<F32, WW, CERT, 1>(fs, fd, sx, e, ks, corr, d2out, seed, thresh, certs, inlier, best);
-      if (!kept) s_list[atomicAdd(&s_cnt[3], 1u)] = (unsigned short)threadIdx.x;
-    }
-    knn_sel_account(sg, t.edge, n_edges, kept != 0, inlier, best, s_cnt);
-    const unsigned int mk = __ballot_sync(0xffffffffu, kept != 0);
-    if ((threadIdx.x & 31) == 0 && mk) atomicAdd(&s_cnt[2], (unsigned int)__popc(mk));
-    __syncthreads();
-    const int n_todo = (int)s_cnt[3];
-    for (int base = threadIdx.x & ~31; base < n_todo; base += blockDim.x) {      // warp-uniform trip count
-      const int i = base + (threadIdx.x & 31);
-      const bool has = i < n_todo;
-      if (has) knn_one<F32, WW, CERT, 2>(fs, fd, sx, e, t.start + (int)s_list[i], corr, d2out, seed, thresh, certs, inlier, best);
-      knn_sel_account(sg, t.edge, n_edges, has, inlier, best, s_cnt);
-    }
-  } else {
-    const bool has = ks < e.n_src;
-    if (has) knn_one<F32, WW, CERT, 0>(fs, fd, sx, e, ks, corr, d2out, seed, thresh, certs, inlier, best);
-    if (SEL) knn_sel_account(sg, t.edge, n_edges, has, inlier, best, s_cnt);
-  }
+  const bool has = ks < e.n_src;
+  if (has) knn_one<F32, WW, CERT, 0>(fs, fd, sx, e, ks, corr, d2out, seed, thresh, certs, inlier, best);
   if (SEL) {   // every thread of the CTA arrives here
+    knn_sel_account(sg, t.edge, n_edges, has, inlier, best, s_cnt);
     __syncthreads();
     if (threadIdx.x == 0) {
       if (s_cnt[0]) atomicAdd(&sg.total[t.edge], s_cnt[0]);
       if (s_cnt[1]) atomicAdd(&sg.below[t.edge], s_cnt[1]);
-      if (CERT == 2 && s_cnt[2]) atomicAdd(&reused[t.edge], (unsigned long long)s_cnt[2]);
+    }
+  }
+}
+
+// ---- certified rounds: two launches instead of knn_kernel -------------------------------------------------------------------------
+// knn_cert_kernel streams over all queries: a query that is still within half its margin of the certified position keeps its match
+// and only recomputes the distance (knn_one, MODE 1); the others are appended to a device-wide list.  knn_todo_kernel then searches
+// and re-certifies the listed queries with every lane busy.  (Searching them inside the first kernel -- even compacted per CTA --
+// measured SLOWER than searching everything: a CTA's finished warps hold their slots while one warp walks the tree, 0.65 vs 0.55 ms.)
+struct CertTodo { int2* list; unsigned int* n; };     // {edge, position in the src frame's tree order}
+
+template <bool F32>
+__global__ void __launch_bounds__(KNN_TILE)
+knn_cert_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
+                const Tile* __restrict__ tiles, int32_t* corr /* aliases seed */, double* __restrict__ d2out,
+                const int32_t* seed, double thresh, SelGuess sg, int n_edges, float4* __restrict__ certs,
+                unsigned long long* __restrict__ reused /* per edge */, CertTodo todo) {
+  const Tile t = tiles[blockIdx.x];
+  const EdgeDev e = edges[t.edge];
+  __shared__ EdgeXf sx;
+  __shared__ unsigned int s_cnt[4];            // inliers | inliers below the window | kept by certificate | to be searched
+  __shared__ unsigned int s_base;
+  __shared__ unsigned short s_list[KNN_TILE];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+  {
+    const double* g = reinterpret_cast<const double*>(xfs + t.edge);
+    double* s = reinterpret_cast<double*>(&sx);
+    for (int i = threadIdx.x; i < (int)(sizeof(EdgeXf) / sizeof(double)); i += blockDim.x) s[i] = g[i];
+  }
+  __syncthreads();
+  const FrameDev fs = frames[e.src];
+  const FrameDev fd = frames[e.dst];
+  const int ks = t.start + threadIdx.x;
+  bool inlier = false; double best = 0.0;
+  int kept = 0;
+  if (ks < e.n_src) {
+    kept = knn_one<F32, true, 1, 1>(fs, fd, sx, e, ks, corr, d2out, seed, thresh, certs, inlier, best);
+    if (!kept) s_list[atomicAdd(&s_cnt[3], 1u)] = (unsigned short)threadIdx.x;
+  }
+  knn_sel_account(sg, t.edge, n_edges, kept != 0, inlier, best, s_cnt);
+  const unsigned int mk = __ballot_sync(0xffffffffu, kept != 0);
+  if ((threadIdx.x & 31) == 0 && mk) atomicAdd(&s_cnt[2], (unsigned int)__popc(mk));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_cnt[0]) atomicAdd(&sg.total[t.edge], s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(&sg.below[t.edge], s_cnt[1]);
+    if (s_cnt[2]) atomicAdd(&reused[t.edge], (unsigned long long)s_cnt[2]);
+    s_base = s_cnt[3] ? atomicAdd(todo.n, s_cnt[3]) : 0u;
+  }
+  __syncthreads();
+  for (unsigned int i = threadIdx.x; i < s_cnt[3]; i += blockDim.x) todo.list[s_base + i] = make_int2(t.edge, t.start + (int)s_list[i]);
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(KNN_TILE, 5)
+knn_todo_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ edges, const EdgeXf* __restrict__ xfs,
+                int32_t* corr /* aliases seed */, double* __restrict__ d2out, const int32_t* seed, double thresh,
+                SelGuess sg, int n_edges, float4* __restrict__ certs, CertTodo todo) {
+  const unsigned int n = *todo.n, lane = threadIdx.x & 31u;
+  for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform
+    const unsigned int i = base + lane;
+    const bool has = i < n;
+    int edge = 0; bool inlier = false; double best = 0.0;
+    if (has) {
+      const int2 it = todo.list[i];
+      edge = it.x;
+      const EdgeDev e = edges[edge];
+      const FrameDev fs = frames[e.src];
+      const FrameDev fd = frames[e.dst];
+      knn_one<F32, true, 1, 2>(fs, fd, xfs[edge], e, it.y, corr, d2out, seed, thresh, certs, inlier, best);
+    }
+    // what the searched queries contribute to the guessed select, summed over the lanes of equal edge first
+    const bool in = has && inlier;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(best);
+    const unsigned long long lo = sg.win[edge], hi = sg.win[(size_t)n_edges + edge];
+    const unsigned int grp = __match_any_sync(0xffffffffu, in ? edge : (int)(0x40000000u | lane));
+    const unsigned int m_lo = __ballot_sync(0xffffffffu, in && key < lo) & grp;
+    if (in && lane == (unsigned int)(__ffs(grp) - 1)) {
+      atomicAdd(&sg.total[edge], (unsigned int)__popc(grp));
+      if (m_lo) atomicAdd(&sg.below[edge], (unsigned int)__popc(m_lo));
+    }
+    if (in && key >= lo && key < hi) {
+      const unsigned int slot = atomicAdd(&sg.cand_n[edge], 1u);
+      if (slot < (unsigned int)SEL_CAP) sg.cand[(size_t)edge * SEL_CAP + slot] = key;
     }
   }
 }

@@ -100,6 +100,7 @@ struct mvicp_ctx {
   DevBuf d_sel_cnt;            // guessed select: [E] inliers | [E] inliers below the guessed window | [1] guesses that missed
   DevBuf d_sel_win;            // [3E] window lo | hi | log2 half-width (select.cuh)
   DevBuf d_certs, d_cert_cnt;  // certificates (knn.cuh, CERT): {position, margin} per slot in tile order; reused queries per edge
+  DevBuf d_todo, d_todo_n;     // certified rounds: the queries that have to be searched after all ({edge, position}), and their number
   bool cert_valid = false;     // every slot's margin belongs to the match in d_corr (the last mvicp_correspond ran with certificates)
   int64_t cert_rounds = 0;
   bool sel_valid = false;      // d_sel holds the previous round's medians (a select ran since the buffers were laid out)
@@ -376,7 +377,7 @@ void mvicp_destroy(mvicp_ctx* c) {
   if (c->comm) ncclCommDestroy(c->comm);
   for (void* p : c->frame_allocs) cudaFree(p);
   DevBuf* bufs[] = {&c->d_frames, &c->d_poses, &c->d_edges, &c->d_xf, &c->d_corr, &c->d_d2, &c->d_count, &c->d_sel, &c->d_hist,
-                    &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_sel_cnt, &c->d_sel_win, &c->d_certs, &c->d_cert_cnt, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
+                    &c->d_weight, &c->d_median, &c->d_selcand, &c->d_selcand_n, &c->d_sel_cnt, &c->d_sel_win, &c->d_certs, &c->d_cert_cnt, &c->d_todo, &c->d_todo_n, &c->d_knn_tiles, &c->d_eval_tiles, &c->d_edge_tile_begin, &c->d_partial,
                     &c->d_state, &c->d_x, &c->d_cand, &c->d_Rt, &c->d_K, &c->d_col, &c->d_H, &c->d_g, &c->d_Hc,
                     &c->d_gc, &c->d_scale, &c->d_diag, &c->d_L, &c->d_rhs, &c->d_step, &c->d_eout,
                     &c->d_hb_ptr, &c->d_hb_row, &c->d_hb_col, &c->d_hc_edge, &c->d_hc_sub, &c->d_gb_ptr, &c->d_gc_edge,
@@ -580,6 +581,9 @@ static int rebuild_work(mvicp_ctx* c) {
   CU(cudaMemset(c->d_sel_cnt.p, 0, sizeof(unsigned int) * (2 * (size_t)E + 1)));
   RET(c->d_sel_win.reserve(sizeof(unsigned long long) * 3 * (size_t)E));
   RET(c->d_certs.reserve(sizeof(float4) * off));
+  RET(c->d_todo.reserve(sizeof(int2) * off));
+  RET(c->d_todo_n.reserve(sizeof(unsigned int)));
+  CU(cudaMemset(c->d_todo_n.p, 0, sizeof(unsigned int)));
   RET(c->d_cert_cnt.reserve(sizeof(unsigned long long) * E));
   CU(cudaMemset(c->d_cert_cnt.p, 0, sizeof(unsigned long long) * E));
   c->cert_valid = false;
@@ -675,10 +679,16 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
     const SelGuess sg = {c->d_sel_win.as<unsigned long long>(), cnt, cnt + E, c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>()};
 #define MV_KNN_ARGS c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(), \
                     c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh
-#define MV_KNN_TAIL sg, E, c->d_certs.as<float4>(), c->d_cert_cnt.as<unsigned long long>()
+#define MV_KNN_TAIL sg, E, c->d_certs.as<float4>()
     if (far && ww) knn_far_kernel<F32, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
     else if (far) knn_far_kernel<F32, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
-    else if (cert == 2) knn_kernel<F32, true, true, 2><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
+    else if (cert == 2) {
+      const CertTodo todo = {c->d_todo.as<int2>(), c->d_todo_n.as<unsigned int>()};
+      knn_cert_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL, c->d_cert_cnt.as<unsigned long long>(), todo);
+      knn_todo_kernel<F32><<<148 * 5, KNN_TILE, 0, c->stream>>>(c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(),
+          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, MV_KNN_TAIL, todo);
+      c->stats.kernel_launches += 1;
+    }
     else if (guess && cert == 1) knn_kernel<F32, true, true, 1><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
     else if (guess) knn_kernel<F32, true, true, 0><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
     else if (cert == 1) knn_kernel<F32, true, false, 1><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);
@@ -696,7 +706,8 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
     unsigned int* cnt = c->d_sel_cnt.as<unsigned int>();
     select_guess_finish_kernel<<<E, SEL_THREADS, 0, c->stream>>>(c->d_edges.as<EdgeDev>(), c->d_corr.as<int32_t>(), c->d_d2.as<double>(),
         c->d_sel.as<SelState>(), cnt, cnt + E, c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>(),
-        c->d_weight.as<float>(), c->d_median.as<double>(), c->d_count.as<unsigned long long>(), c->d_sel_win.as<unsigned long long>(), cnt + 2 * (size_t)E);
+        c->d_weight.as<float>(), c->d_median.as<double>(), c->d_count.as<unsigned long long>(), c->d_sel_win.as<unsigned long long>(), cnt + 2 * (size_t)E,
+        c->d_todo_n.as<unsigned int>());
     c->stats.kernel_launches += 1;
     ++c->sel_guess_rounds;
   } else {

@@ -232,8 +232,9 @@ select_guess_finish_kernel(const EdgeDev* __restrict__ edges, const int32_t* __r
                            SelState* __restrict__ st, unsigned int* __restrict__ total, unsigned int* __restrict__ below,
                            const unsigned long long* __restrict__ cand, unsigned int* __restrict__ cand_n,
                            float* __restrict__ weight, double* __restrict__ median, unsigned long long* __restrict__ edge_count,
-                           unsigned long long* __restrict__ win, unsigned int* __restrict__ misses) {
+                           unsigned long long* __restrict__ win, unsigned int* __restrict__ misses, unsigned int* __restrict__ todo_n) {
   const int e = blockIdx.x;
+  if (e == 0 && threadIdx.x == 0) *todo_n = 0u;   // the certified round's list of searched queries (knn.cuh) has been consumed
   __shared__ unsigned int sh[SEL_BINS];
   __shared__ unsigned long long wtot[SEL_THREADS / 32];
   __shared__ unsigned long long s_prefix, s_rank;

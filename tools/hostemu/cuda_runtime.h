@@ -210,6 +210,7 @@ inline float __double2float_ru(double a) { return hs_up(a); }
 inline float __fsqrt_ru(float a) { return std::nextafterf(hs_up(std::sqrt((double)a)), INFINITY); }
 inline float __fadd_ru(float a, float b) { return hs_up((double)a + (double)b); }
 inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 inline float __fmul_ru(float a, float b) { return hs_up((double)a * (double)b); }
 inline float hs_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
 inline float __fmul_rd(float a, float b) { return hs_down((double)a * (double)b); }

@@ -31,6 +31,7 @@ static inline float __double2float_ru(double a) { return hs_up(a); }
 static inline float __fsqrt_ru(float a) { return std::nextafterf(hs_up(std::sqrt((double)a)), INFINITY); }
 static inline float __fadd_ru(float a, float b) { return hs_up((double)a + (double)b); }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline float __fmul_ru(float a, float b) { return hs_up((double)a * (double)b); }
 static inline float hs_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
@@ -40,6 +41,7 @@ static inline float __fmaf_ru(float a, float b, float c) { return std::nextafter
 static inline void __syncthreads() {}
 // declarations only, so that the kernels' text parses: the host check calls the search functions, never a kernel
 unsigned __ballot_sync(unsigned, int);
+unsigned __match_any_sync(unsigned, int);
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 template <class T> T atomicAdd(T*, T);
 static inline void __syncwarp() {}
