@@ -80,17 +80,17 @@ template <bool F32> static int run(int n, int nq, unsigned seed) {
   FrameDev fd{};
   fd.pts_s = F32 ? (const void*)sf.data() : (const void*)sd.data(); fd.pts_sf = sf.data(); fd.boxes = hb.boxes.data(); fd.faces = hb.faces.data();
   fd.pos_of = hb.pos_of.data(); fd.n = n; fd.n_leaf_pad = hb.n_leaf_pad; fd.depth = hb.depth; fd.absmax = hb.absmax;
-  int bad = 0;
+  int bad = 0; long n_cert = 0, n_pos = 0, n_loose = 0;
   for (int qi = 0; qi < nq; ++qi) {
     // queries: near the surface, far from it, exactly on a point, and outside the bounding box
     const int base = rng() % n; const int kind = qi % 4;
     const double s = kind == 0 ? 1e-4 : (kind == 1 ? 2e-2 : (kind == 2 ? 0.0 : 0.5));
     const double q[3] = {pts[3 * base] + s * G(rng), pts[3 * base + 1] + s * G(rng), pts[3 * base + 2] + s * G(rng)};
-    double best = INFINITY; int bi = INT32_MAX;   // brute force, frame.h:70-76 operation order, lowest index on ties
+    double best = INFINITY, second = INFINITY; int bi = INT32_MAX;   // brute force, frame.h:70-76 operation order, lowest index on ties
     for (int i = 0; i < n; ++i) {
       const double d0 = q[0] - pts[3 * i], d1 = q[1] - pts[3 * i + 1], d2 = q[2] - pts[3 * i + 2];
       const double d = (d0 * d0 + d1 * d1) + d2 * d2;
-      if (d < best) { best = d; bi = i; }
+      if (d < best) { second = best; best = d; bi = i; } else if (d < second) second = d;
     }
     // seeds: none, the right leaf, a random (stale) leaf
     for (int sk = 0; sk < 3; ++sk) {
@@ -102,10 +102,21 @@ template <bool F32> static int run(int n, int nq, unsigned seed) {
         if (s2.bi != bi || s2.best != best) {
           if (++bad < 10) std::printf("MISMATCH q %d kind %d seed-kind %d sched %d: got (%d, %.17g) want (%d, %.17g)\n", qi, kind, sk, sched, s2.bi, s2.best, bi, best);
         }
+        // the certificate of the same search (knn.cuh, CERT): same answer, and its margin never exceeds the true gap to the runner-up
+        NNQueryT st; nn_query_init(st, q[0], q[1], q[2], fd.absmax); nn_track_init(st);
+        nn_search<F32, NNQueryT, true>(fdx, st, start_leaf);
+        const float m = nn_margin(st);
+        const double gap = std::sqrt(second) - std::sqrt(best);
+        if (st.bi != bi || st.best != best || (double)m > gap) {
+          if (++bad < 10) std::printf("CERTIFICATE q %d kind %d seed-kind %d sched %d: got (%d, %.17g, margin %.9g) want (%d, %.17g, gap %.9g)\n", qi, kind, sk, sched, st.bi, st.best, m, bi, best, gap);
+        }
+        if (sk == 1 && kind == 0) { ++n_cert; if (m > 0.f) ++n_pos; else if (n_cert < 400) std::printf("  nonpositive: sched %d gap %.3g margin %.3g  v1 %.9g m1 %.9g m2 %.9g lbmin %.9g best %.9g eaf %.3g bound32 %.9g prune %.9g\n", sched, gap, m, st.v1, st.m1, st.m2, st.lbmin, (float)st.best, st.eaf, st.bound32, st.bound_prune); if (gap > 4e-6 && (double)m < 0.5 * gap - 2e-6) { ++n_loose;
+          if (n_loose < 6) std::printf("  loose: sched %d gap %.3g margin %.3g  v1 %.9g m1 %.9g m2 %.9g lbmin %.9g best %.9g\n", sched, gap, m, st.v1, st.m1, st.m2, st.lbmin, (float)st.best); } }
       }
     }
   }
-  std::printf("n %d queries %d storage %s: %d mismatches\n", n, nq, F32 ? "fp32" : "fp64", bad);
+  std::printf("n %d queries %d storage %s: %d mismatches; certificates of near-surface queries seeded with the right leaf: %ld, margin > 0: %ld, margin below half the true gap: %ld\n",
+              n, nq, F32 ? "fp32" : "fp64", bad, n_cert, n_pos, n_loose);
   return bad;
 }
 
