@@ -109,7 +109,7 @@ knn_far_kernel(const FrameDev* __restrict__ frames, const EdgeDev* __restrict__ 
   }
   nn_search_obb<F32, WW>(fd, ob, nq, start_leaf);
   const double best = nq.best; const int bi = nq.bi;
-  const bool inlier = __dsqrt_rn(best) < thresh;
+  const bool inlier = best <= thresh;   // thresh = cutoff_d2max (knn.cuh)
   corr[e.off + orig] = inlier ? bi : ~bi;
   d2out[e.off + orig] = best;
 }

@@ -7,7 +7,8 @@
 //   * result           the dst point minimising that value      nanoflann.hpp:1200-1247 (exact search, eps = 0);
 //     ties (equal fp64 distance) resolve to the LOWEST ORIGINAL INDEX here, whereas nanoflann keeps the first
 //     point its traversal meets (nanoflann.hpp:1210) -- documented deviation, counted by the tests;
-//   * cutoff           sqrt(d2) < (double)thresh                 frame.cpp:142,156.
+//   * cutoff           sqrt(d2) < (double)thresh                 frame.cpp:142,156 -- evaluated as d2 <= d2max, the largest double
+//                      whose correctly rounded square root is still below the threshold (cutoff_d2max; sqrt is monotone)
 //
 // Search structure: implicit binary AABB tree over leaves in left-balanced KD order (types.cuh), walked in fp32 with a
 // conservative screen and re-ranked in fp64 (see "fp32 screening" below): the answer is the exact fp64 arg-min.
@@ -322,7 +323,7 @@ __device__ __forceinline__ void nn_query_init(NNQuery& s, double qx, double qy, 
 // the certificate allows it (returns 1), otherwise do nothing and return 0 -- the caller searches it later; 2: search (no test).
 template <bool F32, bool WW, int CERT, int MODE>
 __device__ __forceinline__ int knn_one(const FrameDev& fs, const FrameDev& fd, const EdgeXf& sx, const EdgeDev& e, int ks,
-                                       int32_t* corr, double* __restrict__ d2out, const int32_t* seed, double thresh,
+                                       int32_t* corr, double* __restrict__ d2out, const int32_t* seed, double thresh /* cutoff_d2max */,
                                        float4* __restrict__ certs, bool& inlier, double& best) {
   double px, py, pz; int orig;
   Rec<F32>::load(fs.pts_s, ks, px, py, pz, orig);
@@ -341,7 +342,8 @@ __device__ __forceinline__ int knn_one(const FrameDev& fs, const FrameDev& fd, c
   if (seed) {   // previous round's match: a valid first guess, the search stays exact
     const int sd = seed[e.off + orig];
     si = sd >= 0 ? sd : ~sd;
-    if (si >= 0 && si < fd.n) start_leaf = __ldg(fd.pos_of + si) / LEAF; else si = -1;
+    if (!(si >= 0 && si < fd.n)) si = -1;
+    else if (MODE != 1) start_leaf = __ldg(fd.pos_of + si) / LEAF;
   }
   if constexpr (MODE == 1) {
     // displacement since the certificate, rounded up, + the fp32 rounding of both positions (eaf covers it many times over)
@@ -359,7 +361,7 @@ __device__ __forceinline__ int knn_one(const FrameDev& fs, const FrameDev& fd, c
     if constexpr (CERT != 0) certs[e.off + ks] = make_float4(nq.fx, nq.fy, nq.fz, nn_margin(nq));
   }
   best = nq.best; const int bi = nq.bi;
-  inlier = __dsqrt_rn(best) < thresh;
+  inlier = best <= thresh;
   corr[e.off + orig] = inlier ? bi : ~bi;
   d2out[e.off + orig] = best;
   return 1;

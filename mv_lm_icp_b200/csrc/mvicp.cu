@@ -647,8 +647,19 @@ int mvicp_get_graph(mvicp_ctx* c, int32_t* E, int32_t* src, int32_t* dst) {
 }
 
 }  // extern "C"
+// sqrt(d2) < t  <=>  d2 <= the largest double whose correctly rounded square root is below t (sqrt is monotone, IEEE on both sides)
+static double cutoff_d2max(float thresh) {
+  const double t = (double)thresh;
+  if (!(t > 0.0)) return -1.0;                  // nothing is an inlier (also for a NaN threshold)
+  if (std::isinf(t)) return std::numeric_limits<double>::max();
+  double x = t * t;
+  while (x > 0.0 && !(std::sqrt(x) < t)) x = std::nextafter(x, 0.0);
+  while (std::sqrt(std::nextafter(x, std::numeric_limits<double>::infinity())) < t) x = std::nextafter(x, std::numeric_limits<double>::infinity());
+  return std::sqrt(x) < t ? x : -1.0;
+}
 template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
   const int E = c->E;
+  const double d2max = cutoff_d2max(thresh);
   const bool seed = c->have_corr && !(c->flags & MVICP_FLAG_NO_SEED);
   bool guess = false, far = false;
   int cert = 0;
@@ -678,7 +689,7 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
     unsigned int* cnt = c->d_sel_cnt.as<unsigned int>();
     const SelGuess sg = {c->d_sel_win.as<unsigned long long>(), cnt, cnt + E, c->d_selcand.as<unsigned long long>(), c->d_selcand_n.as<unsigned int>()};
 #define MV_KNN_ARGS c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(), c->d_knn_tiles.as<Tile>(), \
-                    c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, (double)thresh
+                    c->d_corr.as<int32_t>(), c->d_d2.as<double>(), seed ? c->d_corr.as<int32_t>() : nullptr, d2max
 #define MV_KNN_TAIL sg, E, c->d_certs.as<float4>()
     if (far && ww) knn_far_kernel<F32, true><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
     else if (far) knn_far_kernel<F32, false><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, c->d_obb.as<ObbDev>());
@@ -686,7 +697,7 @@ template <bool F32> static int launch_correspond(mvicp_ctx* c, float thresh) {
       const CertTodo todo = {c->d_todo.as<int2>(), c->d_todo_n.as<unsigned int>()};
       knn_cert_kernel<F32><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL, c->d_cert_cnt.as<unsigned long long>(), todo);
       knn_todo_kernel<F32><<<148 * 5, KNN_TILE, 0, c->stream>>>(c->d_frames.as<FrameDev>(), c->d_edges.as<EdgeDev>(), c->d_xf.as<EdgeXf>(),
-          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), (double)thresh, MV_KNN_TAIL, todo);
+          c->d_corr.as<int32_t>(), c->d_d2.as<double>(), c->d_corr.as<int32_t>(), d2max, MV_KNN_TAIL, todo);
       c->stats.kernel_launches += 1;
     }
     else if (guess && cert == 1) knn_kernel<F32, true, true, 1><<<c->n_knn_tiles, KNN_TILE, 0, c->stream>>>(MV_KNN_ARGS, MV_KNN_TAIL);

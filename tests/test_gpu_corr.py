@@ -308,6 +308,28 @@ def test_guessed_median_select_degenerate_buckets(oracle):
     eng.close()
 
 
+def test_cutoff_boundary_is_the_reference_comparison(oracle):
+    """`sqrt(d2) < cutoff` (frame.cpp:142,156) is evaluated on the device as d2 <= the largest double whose square root is below the
+    cutoff: points within a few ulps of the cutoff distance, on both sides, must be classified as the oracle's sqrt comparison does."""
+    for cutoff in (np.float32(0.05), np.float32(0.3), np.float32(1e-3)):
+        t = float(cutoff)
+        xs = [t * (1.0 + k * 2.0 ** -52) for k in range(-6, 7)] + [np.nextafter(t, 0), np.nextafter(t, 1), t, 0.5 * t, 2 * t]
+        src = np.array([[x, 0.0, 0.0] for x in xs] + [[0.0, x, 0.0] for x in xs] + [[x / np.sqrt(3), x / np.sqrt(3), x / np.sqrt(3)] for x in xs])
+        pts = [np.zeros((1, 3)), src]
+        edges = [(1, 0)]
+        eng = Engine(); eng.set_frames(pts, None); eng.set_graph(edges); eng.set_poses([np.eye(4)] * 2)
+        eng.correspond(float(cutoff))
+        ref = []
+        for s_, d_ in edges:
+            idx = oracle.KdIndex(pts[d_], "brute")
+            i, d2 = idx.closest_points(pts[s_], np.eye(4), np.eye(4))
+            f, sec, dist, w, med = oracle.filter_edge(i, d2, cutoff)
+            ref.append(dict(first=f, second=sec, dist=dist, weight=w, nn_idx=i, nn_d2=d2, median=med))
+        _check_edges(eng, ref, edges)
+        assert 0 < len(ref[0]["first"]) < len(src)
+        eng.close()
+
+
 def test_closest_point_api(oracle):
     sc = scene(4, 5000, 21)
     eng = Engine(); eng.set_frames(sc["pts"], sc["nor"])

@@ -59,6 +59,7 @@ def test_correspondence_step(emu, oracle, golden_dir):
     T.test_closest_point_api(oracle)
     T.test_all_edges_in_one_call_equal_the_per_edge_lists(oracle)
     T.test_guessed_median_select_is_exact(oracle)
+    T.test_cutoff_boundary_is_the_reference_comparison(oracle)
     T.test_guessed_median_select_degenerate_buckets(oracle)
     T.test_certified_matches_are_exact(oracle)
     T.test_certificates_with_ties_and_duplicates(oracle)
