@@ -354,16 +354,21 @@ def run_ours(args, cfg):
             _, nms = eng.recompute_normals(10, fetch=False)      # Frame::recomputeNormals (main_multiview.cpp:68)
         eng.set_poses(sc["poses_init"])
         eng.set_graph(edges)
+        comm_s = 0.0
         if with_comm and world > 1:
+            eng.sync(); t1 = time.perf_counter()
             idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
                 idt.copy_(torch.frombuffer(bytearray(mv.nccl_unique_id()), dtype=torch.uint8))
             dist.broadcast(idt, 0)
             eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+            eng.sync(); comm_s = time.perf_counter() - t1
         eng.sync()
-        return eng, time.perf_counter() - t0, nms
+        make_engine.comm_s = comm_s      # NCCL communicator + peer-memory mapping: once per process group, not per scene
+        return eng, time.perf_counter() - t0 - comm_s, nms
 
     eng, setup_s, normals_ms = make_engine(True)
+    comm_init_s = make_engine.comm_s
     # Frame::recomputeNormals (default-on in the reference, before round 0; not part of the metric): timed once, on a
     # scratch engine so that the synthetic benchmark itself keeps the uploaded fp32-exact normals
     if rank == 0 and world == 1 and normals_ms is None and not args.no_normals:
@@ -503,7 +508,7 @@ def run_ours(args, cfg):
                                 ((sum(n_pts) * 48 + n_q * 12) / 1e6),
                           "parallelism": f"edges (frame -> neighbour query sets) sharded over {world} GPU(s), one process per GPU",
                           "timing": "wall clock between barriers (host-driven LM loop); device-event sum = %.3f ms/step" % (dev_ms / K),
-                          "setup_ms_excluded": setup_s * 1e3,
+                          "setup_ms_excluded": setup_s * 1e3, "comm_init_ms_excluded": comm_init_s * 1e3,
                           "normals_ms_excluded": normals_ms,
                           "per_round_ms": [round(p["ms"], 3) for p in per],
                           "per_round_knn_ms": [round(p["knn_ms"], 3) for p in per],
