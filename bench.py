@@ -490,7 +490,7 @@ def run_ours(args, cfg):
         share = {"knn": sum(p["knn_ms"] for p in per) / dev_ms, "select": sum(p["select_ms"] for p in per) / dev_ms,
                  "lm_eval": lm_eval_ms / dev_ms, "lm_other": sum(p["lm_other_ms"] for p in per) / dev_ms}
         dominant = "knn" if share["knn"] >= share["lm_eval"] else "lm_eval"
-        knn_name = "knn_kernel"
+        knn_name = "knn_kernel"      # the NN step of a round: knn_far_kernel (rounds 0-1), knn_kernel, or knn_cert_kernel + knn_todo_kernel (certified rounds)
         roof_knn = {"kernel": knn_name, "bound": "hbm", "achieved": knn_gbs, "peak": peak, "unit": "GB/s", "frac": knn_gbs / peak,
                     "traffic": measured_traffic(knn_name) if world == 1 else None, "algorithmic_bytes_per_launch": knn_bytes,
                     "avg_launch_ms": knn_ms, "peak_source": peak_src,
