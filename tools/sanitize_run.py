@@ -7,11 +7,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mv_lm_icp_b200 as mv
 from mv_lm_icp_b200 import synth
-from mv_lm_icp_b200.api import FLAG_NO_OBB, FLAG_NO_SEED, ICP_Ceres
+from mv_lm_icp_b200.api import FLAG_HOST_BUILD, FLAG_NO_ADJ, FLAG_NO_OBB, FLAG_NO_SEED, ICP_Ceres, default_options
 
 sc = synth.make_scene(4, 1501, config_id=1)
 edges = synth.ring_edges(4, 2)
-for flags in (0, FLAG_NO_SEED, FLAG_NO_OBB):
+for flags in (0, FLAG_NO_SEED, FLAG_NO_OBB, FLAG_HOST_BUILD | FLAG_NO_ADJ):
     eng = mv.Engine(device=0, flags=flags)
     eng.set_frames(sc["pts"], sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_init"])
     for param in (mv.PARAM_SE3, mv.PARAM_QUAT, mv.PARAM_AA):
@@ -22,6 +22,20 @@ for flags in (0, FLAG_NO_SEED, FLAG_NO_OBB):
     eng.closest_point(1, sc["pts"][2][7])
     eng.recompute_normals(10); eng.knn_self(0, 5)
     eng.icp_round(0.05, mv.PARAM_SE3, mv.COST_P2PLANE, True)
+    eng.close()
+# converged rounds: guessed select, certificates written, then certified rounds (streaming kernel + searched list), both storages
+none = default_options(); none.max_num_iterations = 0
+for cloud in (sc["pts"], [p + np.random.default_rng(4).normal(0, 1e-9, p.shape) for p in sc["pts"]]):
+    eng = mv.Engine(device=0)
+    eng.set_frames(cloud, sc["nor"]); eng.set_graph(edges); eng.set_poses(sc["poses_gt"])
+    eng.correspond(0.05); eng.optimize(options=none)
+    for _ in range(4):
+        eng.correspond(0.05)
+    one = default_options(); one.max_num_iterations = 1
+    for _ in range(3):
+        eng.optimize(options=one); eng.correspond(0.05)
+    st = eng.stats(); assert st["cert_rounds"] >= 2 and st["select_guess_rounds"] >= 2, st
+    eng.pull_all_edges()
     eng.close()
 # fp64 storage (coordinates not fp32-representable) + non-rigid poses (general LM path)
 rng = np.random.default_rng(3)
