@@ -75,6 +75,63 @@ def one(seed):
     return M, flags
 
 
+def one_steady(seed):
+    """Converged-round shortcuts (guessed median select, certified matches) on the random shapes of one(): rounds whose previous
+    solve took 0 or 1 LM iterations, compared bit for bit with an engine that has both shortcuts switched off, and with the oracle
+    at the end.  Degenerate clouds (exact ties, duplicates, single points) must never certify a wrong match."""
+    from mv_lm_icp_b200.api import FLAG_NO_CERT, FLAG_NO_SELECT_GUESS, default_options
+    rng = np.random.default_rng(50_000 + seed)
+    M = int(rng.integers(2, 5))
+    scale = float(rng.choice([1e-3, 1.0, 1e3])); offset = rng.normal(0, 1, 3) * scale * float(rng.choice([0, 1, 100]))
+    f32 = bool(rng.integers(0, 2))
+    pts = []
+    for v in range(M):
+        n = int(rng.choice([1, 2, 7, 8, 9, 33, 500, 3000]))
+        p = cloud(rng, int(rng.integers(0, 5)), n, scale, offset)
+        pts.append(p.astype(np.float32).astype(np.float64) if f32 else p)
+    poses = []
+    for v in range(M):
+        P = np.eye(4); P[:3, :3] = rot(rng, 0.02); P[:3, 3] = rng.normal(0, 0.01, 3) * scale
+        poses.append(P)
+    poses[0] = np.eye(4)
+    edges = [(s, d) for s in range(M) for d in range(M) if s != d and rng.integers(0, 2)] or [(1, 0)]
+    thresh = float(rng.choice([0.05, 0.5, 5.0])) * scale
+    base = int(rng.choice([0, 4, 8, 16]))
+    engs = [Engine(flags=base), Engine(flags=base | FLAG_NO_CERT | FLAG_NO_SELECT_GUESS)]
+    opts = []
+    for it in (0, 1, 1, 0, 1, 1):
+        o = default_options(); o.max_num_iterations = it; opts.append(o)
+    for eng in engs:
+        eng.set_frames(pts, None); eng.set_graph(edges); eng.set_poses(poses)
+    for rnd, o in enumerate(opts):
+        out = []
+        for eng in engs:
+            eng.correspond(thresh)
+            out.append(([eng.get_nn(e) for e in range(len(edges)) if edges[e][0] != 0], [eng.get_edge(e, arrays=False) for e in range(len(edges))]))
+            try:
+                eng.optimize(cost=0, options=o)
+            except Exception as ex:      # a degenerate system may be rejected; both engines must then agree on that too
+                out[-1] = out[-1] + (str(ex),)
+        assert len(out[0]) == len(out[1]), (seed, rnd, out[0][2:], out[1][2:])
+        for (i0, d0), (i1, d1) in zip(out[0][0], out[1][0]):
+            assert np.array_equal(i0, i1) and np.array_equal(d0.view(np.uint64), d1.view(np.uint64)), (seed, rnd, "nn")
+        assert out[0][1] == out[1][1], (seed, rnd, "count / weight")
+        assert np.array_equal(np.asarray(engs[0].get_poses()).view(np.uint64), np.asarray(engs[1].get_poses()).view(np.uint64)), (seed, rnd, "poses")
+    P = engs[0].get_poses()
+    if np.all(np.isfinite(P)):
+        engs[0].correspond(thresh)
+        ref = oracle_correspond(O, pts, P, edges, thresh=np.float32(thresh), threads=4)
+        for e, r in enumerate(ref):
+            if r is None:
+                continue
+            i, d2 = engs[0].get_nn(e)
+            assert np.array_equal(d2.view(np.uint64), r["nn_d2"].view(np.uint64)) and np.array_equal(i, r["nn_idx"]), (seed, e, "oracle")
+    st = engs[0].stats()
+    for eng in engs:
+        eng.close()
+    return M, base, st["select_guess_rounds"], st["cert_rounds"], st["cert_reused"]
+
+
 def one_lm(seed):
     """LM step on a well-posed random scene: same termination, iteration counts and poses (1e-8) as the oracle."""
     from mv_lm_icp_b200 import synth
@@ -108,3 +165,5 @@ if __name__ == "__main__":
         print("seed", seed, "ok", info, flush=True)
         if seed % 4 == 0:
             print("seed", seed, "lm ok", one_lm(seed), flush=True)
+        if seed % 2 == 0:
+            print("seed", seed, "steady ok", one_steady(seed), flush=True)
