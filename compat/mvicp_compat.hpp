@@ -32,8 +32,14 @@ struct Session {
   std::vector<int32_t> e_src, e_dst;
   bool corr_valid = false, graph_pushed = false;
   struct Rec { int32_t first, second; double dist; };   // == struct Correspondance (frame.h:18-22)
-  std::vector<Rec> records;                              // staging of mvicp_get_all_edges
-  ~Session() { mvicp_destroy(ctx); }
+  Rec* records = nullptr; int64_t records_cap = 0;       // page-locked staging of mvicp_get_all_edges (mvicp_host_alloc)
+  ~Session() { mvicp_host_free(records); mvicp_destroy(ctx); }
+  void reserve_records(int64_t cap) {
+    if (cap <= records_cap) return;
+    mvicp_host_free(records); records = nullptr; records_cap = 0;
+    void* p = nullptr; check(mvicp_host_alloc(sizeof(Rec) * (size_t)cap, &p));
+    records = static_cast<Rec*>(p); records_cap = cap;
+  }
 
   void bind(const std::vector<std::shared_ptr<FrameT>>& fr) {
     if (ctx && frames == &fr) return;
@@ -91,8 +97,8 @@ void computeClosestPoints(Session<FrameT>& s, std::vector<std::shared_ptr<FrameT
   int32_t E = 0; for (auto& f : frames) E += (int32_t)f->neighbours.size();
   std::vector<int64_t> off(E + 1); std::vector<float> w(E);
   int64_t cap = 0; for (auto& f : frames) cap += (int64_t)f->neighbours.size() * (int64_t)f->pts.size();
-  if (materialize) s.records.resize((size_t)cap);
-  check(mvicp_get_all_edges(s.ctx, materialize ? (void*)s.records.data() : nullptr, cap, off.data(), w.data()));
+  if (materialize) s.reserve_records(cap);
+  check(mvicp_get_all_edges(s.ctx, materialize ? (void*)s.records : nullptr, cap, off.data(), w.data()));
   int32_t e = 0;
   for (auto& f : frames)
     for (auto& ne : f->neighbours) {

@@ -137,6 +137,11 @@ int mvicp_get_edge(mvicp_ctx* ctx, int32_t e, int32_t* first, int32_t* second, d
  * weights[e] = OutgoingEdge::weight.  offsets has n_edges + 1 entries; out_records may be NULL (counts and weights only) and
  * otherwise holds `capacity` records (sum of the src cloud sizes always suffices).  Built on the device, one copy back. */
 int mvicp_get_all_edges(mvicp_ctx* ctx, void* out_records, int64_t capacity, int64_t* offsets, float* weights /*nullable*/);
+/* Page-locked host memory for the arrays a caller hands to mvicp_get_all_edges / mvicp_get_edge / mvicp_get_nn: copies into it run at
+ * the link's speed instead of through the driver's staging buffer (config 3: 121 MB of records per round).  Any host pointer works;
+ * this is an allocation helper, not a requirement. */
+int mvicp_host_alloc(size_t bytes, void** out);
+int mvicp_host_free(void* p);
 /* Raw nearest neighbour of every src point of edge e (before the cutoff): index + squared distance, i.e. what
  * Frame::getClosestPoint returns per query (frame.cpp:187-206). */
 int mvicp_get_nn(mvicp_ctx* ctx, int32_t e, int32_t* nn_idx, double* nn_d2);

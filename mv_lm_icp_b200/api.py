@@ -54,8 +54,15 @@ class Engine:
         self.n_pts = []
         self._keep = None
 
+    def _free_pinned(self):
+        if getattr(self, "_rec_ptr", None) is not None and self._rec_ptr.value:
+            self.host_edges = None; self._rec_buf = None
+            self._l.mvicp_host_free(self._rec_ptr)
+        self._rec_ptr = None
+
     def close(self):
         if self._ctx:
+            self._free_pinned()
             self._l.mvicp_destroy(self._ctx)
             self._ctx = C.c_void_p()
 
@@ -132,7 +139,11 @@ class Engine:
         cap = sum(self.n_pts[s] for s, _ in self.edges)
         if records:
             if getattr(self, "_rec_buf", None) is None or len(self._rec_buf) < cap:
-                self._rec_buf = np.empty(cap, self.CORR_DTYPE)
+                self._free_pinned()
+                ptr = C.c_void_p()
+                check(self._l.mvicp_host_alloc(C.c_size_t(cap * self.CORR_DTYPE.itemsize), C.byref(ptr)))   # page-locked: the copy runs at link speed
+                self._rec_ptr = ptr
+                self._rec_buf = np.frombuffer((C.c_char * (cap * self.CORR_DTYPE.itemsize)).from_address(ptr.value), dtype=self.CORR_DTYPE) if cap else np.empty(0, self.CORR_DTYPE)
             check(self._l.mvicp_get_all_edges(self._ctx, self._rec_buf.ctypes.data_as(C.c_void_p), C.c_int64(cap), _p(off, C.c_int64), _p(w, C.c_float)))
             self.host_edges = [(self._rec_buf[off[e]:off[e + 1]], w[e]) for e in range(E)]
         else:

@@ -827,6 +827,18 @@ int mvicp_get_all_edges(mvicp_ctx* c, void* out_records, int64_t capacity, int64
   return MVICP_OK;
 }
 
+int mvicp_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(MVICP_ERR_INVALID, "mvicp_host_alloc: bad arguments");
+  *out = nullptr;
+  if (!bytes) return MVICP_OK;
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return MVICP_OK;
+}
+int mvicp_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return MVICP_OK;
+}
+
 int mvicp_get_nn(mvicp_ctx* c, int32_t e, int32_t* nn_idx, double* nn_d2) {
   if (!c || e < 0 || e >= c->E) return fail(MVICP_ERR_INVALID, "mvicp_get_nn: bad edge");
   CU(cudaSetDevice(c->device));

@@ -222,7 +222,7 @@ inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 typedef int cudaError_t; typedef void* cudaStream_t; typedef void* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorNotReady = 600, cudaErrorNotSupported = 801 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-enum { cudaStreamNonBlocking = 1, cudaHostAllocMapped = 2, cudaIpcMemLazyEnablePeerAccess = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocMapped = 2, cudaHostAllocPortable = 1, cudaIpcMemLazyEnablePeerAccess = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
 inline cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 256, n ? n : 1) ? 2 : cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
