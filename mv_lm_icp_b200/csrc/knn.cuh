@@ -12,6 +12,15 @@
 //
 // Search structure: implicit binary AABB tree over leaves in left-balanced KD order (types.cuh), walked in fp32 with a
 // conservative screen and re-ranked in fp64 (see "fp32 screening" below): the answer is the exact fp64 arg-min.
+//
+// Shortcuts, all exact (same index, same fp64 distance as the plain search; each with a flag that switches it off, mvicp.h):
+//   * seeds            the previous round's match names the leaf the search starts in (nn_search);
+//   * neighbour lists  a seeded query inside its start leaf's reach looks at that leaf and its listed neighbours only (nn_adj_fast);
+//   * certificates     a search also reports the margin by which its match wins (nn_margin); in converged rounds a query that stayed
+//                      within half that margin keeps its match without a search (knn_cert_kernel), the rest is searched densely
+//                      (knn_todo_kernel);
+//   * select epilogue  in converged rounds the kernels also count the inliers below / collect the keys inside a window around the
+//                      previous median, which replaces the passes of the median select (knn_sel_account, select.cuh).
 #pragma once
 #include <cuda_runtime.h>
 #include <limits.h>
